@@ -1,0 +1,51 @@
+# Top-level build: the CUDA library (sm_100a only), the C host programs, the oracle.
+NVCC      ?= nvcc
+CC        ?= gcc
+ARCH       = -gencode arch=compute_100a,code=sm_100a
+NVFLAGS    = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -cudart static
+CFLAGS     = -std=c11 -Wall -Wextra -O2
+LIBDIR     = tiny_mc_b200/lib
+BINDIR     = tiny_mc_b200/bin
+CSRC       = tiny_mc_b200/csrc
+HOST       = tiny_mc_b200/host
+LIB        = $(LIBDIR)/libtinymc_b200.so
+# -D overrides for the host programs, e.g. make headless DEFS="-DPHOTONS=67108864 -DSEED=7"
+DEFS      ?=
+
+all: lib host oracle
+
+lib: $(LIB) $(LIBDIR)/libtmc_report.so $(BINDIR)/tmc_microbench
+
+$(LIB): $(CSRC)/tmc_api.cu $(CSRC)/walk_kernel.cuh $(CSRC)/philox.cuh include/tiny_mc_b200.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/tmc_api.cu -ldl
+
+# the printout formatter alone, so tests can feed it reference tallies (no GPU needed)
+$(LIBDIR)/libtmc_report.so: $(HOST)/report.c $(HOST)/report.h
+	@mkdir -p $(LIBDIR)
+	$(CC) $(CFLAGS) -fPIC -shared -o $@ $(HOST)/report.c -lm
+
+$(BINDIR)/tmc_microbench: $(CSRC)/microbench.cu
+	@mkdir -p $(BINDIR)
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<
+
+host: $(BINDIR)/headless $(LIBDIR)/libphoton_compat.so
+
+$(BINDIR)/headless: $(HOST)/tiny_mc.c $(HOST)/report.c $(HOST)/wtime.c $(LIB)
+	@mkdir -p $(BINDIR)
+	$(CC) $(CFLAGS) $(DEFS) -Iinclude -I$(HOST) -o $@ $(HOST)/tiny_mc.c $(HOST)/report.c $(HOST)/wtime.c \
+	    -L$(LIBDIR) -ltinymc_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
+
+$(LIBDIR)/libphoton_compat.so: $(HOST)/photon_compat.c $(LIB)
+	$(CC) $(CFLAGS) $(DEFS) -Iinclude -I$(HOST) -fPIC -shared -o $@ $(HOST)/photon_compat.c \
+	    -L$(LIBDIR) -ltinymc_b200 -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -C oracle all
+	@if [ -d /root/reference ]; then $(MAKE) -C oracle ref; fi
+
+clean:
+	rm -rf $(LIBDIR) $(BINDIR)
+	$(MAKE) -C oracle clean
+
+.PHONY: all lib host oracle clean

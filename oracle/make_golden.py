@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""oracle/make_golden.py — TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+
+Regenerates tests/golden/*.json|npz from the UNMODIFIED reference object code in oracle/_ref
+(run `make -C oracle ref` first; needs /root/reference, so this runs in the build container
+only — the fixtures are what travels to the GPU box and into git).
+
+  ref_float_tallies.json   reference driver semantics (tiny_mc.c:43,47-49): srand(seed), N calls
+                           of photon() into ONE pair of float arrays; the float bits, per config.
+                           Pins oracle/photon_port.c bit for bit.
+  ref_batches_<cfg>.npz    B independent srand seeds x n photons, 256-photon float chunks summed
+                           in double: per-batch heat / heat2.  The statistical
+                           reference for the GPU parity tests (batch-means sigma).
+  port_xoshiro_batches_<cfg>.npz  the same batches from oracle/photon_port.c (pinned to the
+                           reference bit for bit) driven by xoshiro256** instead of glibc rand():
+                           the high-statistics reference, free of rand()'s lag-3/31 correlation.
+  headless_asshipped.txt   stdout of the reference `headless` built exactly as its Makefile does,
+                           SEED=20141017; with ref_float_tallies.json["headless"] (same seed, same
+                           32768 photons) it pins the printout formatter byte for byte.
+"""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import pyoracle as orc  # noqa: E402
+
+GOLD = Path(__file__).resolve().parent.parent / "tests" / "golden"
+HEADLESS_SEED = 20141017
+
+
+def bits(a):
+    return [int(v) for v in np.asarray(a, np.float32).view(np.uint32)]
+
+
+def main():
+    assert orc.have_ref(), "run `make -C oracle ref` first"
+    GOLD.mkdir(parents=True, exist_ok=True)
+
+    exact = {}
+    for name, seed, n in (("default", 1234, 4096), ("highalbedo", 99, 64), ("finegrid", 4321, 4096)):
+        r = orc.run_batch(name, seed, n, chunk=0, impl="reference")
+        nz = np.nonzero(r["heat_f"])[0]
+        exact[name] = dict(config=orc.CONFIGS[name], seed=seed, photons=n,
+                           nonzero_shells=[int(i) for i in nz],
+                           heat_bits=bits(r["heat_f"][nz]), heat2_bits=bits(r["heat2_f"][nz]))
+    r = orc.run_batch("default", HEADLESS_SEED, 32768, chunk=0, impl="reference")
+    exact["headless"] = dict(config=orc.CONFIGS["default"], seed=HEADLESS_SEED, photons=32768,
+                             heat_bits=bits(r["heat_f"]), heat2_bits=bits(r["heat2_f"]))
+    (GOLD / "ref_float_tallies.json").write_text(json.dumps(exact))
+
+    out = subprocess.run([str(orc.REF_DIR / "headless_asshipped")], capture_output=True, text=True, check=True).stdout
+    (GOLD / "headless_asshipped.txt").write_text(out)
+
+    plans = (("default", 64, 1 << 16), ("highalbedo", 64, 1 << 10), ("finegrid", 64, 1 << 16))
+    for name, nb, n in plans:
+        seeds = [1000 + 7 * b for b in range(nb)]
+        heat, heat2, _, secs, wall = orc.run_batches(name, seeds, n, chunk=256, impl="reference")
+        if name == "finegrid":   # 16384 shells x 64 batches is too big to commit: keep 128-shell groups
+            heat = heat.reshape(nb, 128, 128).sum(axis=2)
+            heat2 = heat2.reshape(nb, 128, 128).sum(axis=2)
+        np.savez_compressed(GOLD / f"ref_batches_{name}.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
+                            photons_per_batch=n, chunk=256)
+        print(f"{name}: {nb} x {n} photons, cpu {secs.sum():.1f} s, wall {wall:.1f} s, "
+              f"total/photon {heat.sum() / (nb * n):.6f}")
+        # the same walk code (photon_port.c, pinned to the reference above) on a sound generator
+        heat, heat2, _, secs, wall = orc.run_batches(name, seeds, n, chunk=256, impl="port", rng="xoshiro")
+        if name == "finegrid":
+            heat = heat.reshape(nb, 128, 128).sum(axis=2)
+            heat2 = heat2.reshape(nb, 128, 128).sum(axis=2)
+        np.savez_compressed(GOLD / f"port_xoshiro_batches_{name}.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
+                            photons_per_batch=n, chunk=256)
+        print(f"{name} (xoshiro): total/photon {heat.sum() / (nb * n):.6f}")
+
+
+if __name__ == "__main__":
+    main()

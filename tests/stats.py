@@ -1,0 +1,29 @@
+"""Statistical comparison helpers for the parity tests."""
+import numpy as np
+
+
+def batch_means_z(a_batches, a_n, b_batches, b_n, min_mean=0.0):
+    """Per-shell z of the difference of per-photon means, sigma from batch means on both sides.
+
+    a_batches, b_batches: [B, S] tallies (weight units) of batches of a_n / b_n photons each.
+    """
+    a = np.asarray(a_batches, np.float64) / a_n
+    b = np.asarray(b_batches, np.float64) / b_n
+    ma, mb = a.mean(axis=0), b.mean(axis=0)
+    va = a.var(axis=0, ddof=1) / a.shape[0]
+    vb = b.var(axis=0, ddof=1) / b.shape[0]
+    sd = np.sqrt(va + vb)
+    ok = (sd > 0) & (np.maximum(ma, mb) > min_mean)
+    z = np.zeros_like(ma)
+    z[ok] = (ma[ok] - mb[ok]) / sd[ok]
+    return z, ok
+
+
+def literal_sigma_z(heat_a, heat2_a, n_a, heat_b, heat2_b, n_b):
+    """The contract's literal statistic: sigma derived from heat2 as reference tiny_mc.c:64 does,
+    sigma_X^2 = (heat2_X - heat_X^2 / N_X) / N_X^2.  NaN where that variance is negative (H5)."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        va = (heat2_a - heat_a**2 / n_a) / n_a**2
+        vb = (heat2_b - heat_b**2 / n_b) / n_b**2
+        z = (heat_a / n_a - heat_b / n_b) / np.sqrt(va + vb)
+    return z

@@ -1,0 +1,321 @@
+// microbench.cu — issue-rate micro-benchmarks for the pipes the photon walk lives on.
+//
+// MEASURED_PEAKS.json holds HBM and bf16 tensor peaks only; this path is bound by the FP32/INT
+// issue rate, the MUFU (XU) pipe and the shared-memory atomic unit.  This program
+// measures those denominators on the actual B200: warp-instructions per clock per SM for each
+// SASS opcode class the kernel uses, for the mixes it issues (FMA pipe + ALU pipe), for a whole
+// Philox4x32-10 block, and for ATOMS.ADD under the address patterns of the three tally regimes.
+//
+// Output: one JSON object per line on stdout:
+//   {"test": "...", "warp_inst_per_clk_per_sm": x, "lanes_per_clk_per_sm": 32x, "sm_mhz": f, ...}
+// Cycle counts come from clock64() inside the kernel (mean over blocks), so they are
+// independent of DVFS; the MHz figure is cycles / CUDA-event time.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x)                                                                           \
+    do {                                                                                \
+        cudaError_t e_ = (x);                                                           \
+        if (e_ != cudaSuccess) {                                                        \
+            fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_));                    \
+            exit(2);                                                                    \
+        }                                                                               \
+    } while (0)
+
+constexpr int kBlock = 256;
+constexpr int kIters = 2048;   // outer loop trips
+constexpr int kChains = 8;     // independent dependency chains per thread
+
+struct Out {
+    long long cycles;
+    unsigned sink;
+};
+
+#define REP8(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+
+// ---- generic harness: BODY is a statement list executed kIters times -----------------------
+#define BENCH_KERNEL(NAME, DECLS, BODY, SINK)                                            \
+    __global__ void __launch_bounds__(kBlock) NAME(Out* out, unsigned seed)              \
+    {                                                                                    \
+        DECLS;                                                                           \
+        __syncthreads();                                                                 \
+        const long long t0 = clock64();                                                  \
+        _Pragma("unroll 1") for (int it = 0; it < kIters; ++it) { BODY; }                \
+        const long long t1 = clock64();                                                  \
+        __syncthreads();                                                                 \
+        if (threadIdx.x == 0) out[blockIdx.x].cycles = t1 - t0;                          \
+        if ((SINK) == 0x12345u) out[blockIdx.x].sink = 1;                                \
+    }
+
+#define F_DECL float f0 = seed * 1e-9f + threadIdx.x, f1 = f0 + 1, f2 = f0 + 2, f3 = f0 + 3, f4 = f0 + 4, f5 = f0 + 5, f6 = f0 + 6, f7 = f0 + 7; const float ca = 1.0001f + seed * 1e-12f, cb = 0.5f
+#define U_DECL unsigned u0 = seed + threadIdx.x, u1 = u0 * 3 + 1, u2 = u0 * 5 + 2, u3 = u0 * 7 + 3, u4 = u0 * 11 + 4, u5 = u0 * 13 + 5, u6 = u0 * 17 + 6, u7 = u0 * 19 + 7; const unsigned ka = seed | 0xD2511F53u, kb = seed ^ 0x9E3779B9u
+#define F_SINK __float_as_uint(f0 + f1 + f2 + f3 + f4 + f5 + f6 + f7)
+#define U_SINK (u0 ^ u1 ^ u2 ^ u3 ^ u4 ^ u5 ^ u6 ^ u7)
+
+#define FFMA_(i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f##i) : "f"(ca), "f"(cb));
+BENCH_KERNEL(k_ffma, F_DECL, REP8(FFMA_) REP8(FFMA_), F_SINK)
+
+#define FMUL_(i) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(f##i) : "f"(ca));
+BENCH_KERNEL(k_fmul, F_DECL, REP8(FMUL_) REP8(FMUL_), F_SINK)
+
+#define FADD_(i) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f##i) : "f"(cb));
+BENCH_KERNEL(k_fadd, F_DECL, REP8(FADD_) REP8(FADD_), F_SINK)
+
+// packed FP32x2 (Blackwell): two FMAs per lane per instruction
+#define FFMA2_DECL F_DECL; unsigned long long p0, p1, p2, p3, pc, pd; \
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p0) : "f"(f0), "f"(f1)); \
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p1) : "f"(f2), "f"(f3)); \
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p2) : "f"(f4), "f"(f5)); \
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p3) : "f"(f6), "f"(f7)); \
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(pc) : "f"(ca)); \
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(pd) : "f"(cb))
+#define FFMA2_(i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p##i) : "l"(pc), "l"(pd));
+#define REP4(X) X(0) X(1) X(2) X(3)
+BENCH_KERNEL(k_ffma2, FFMA2_DECL, REP4(FFMA2_) REP4(FFMA2_) REP4(FFMA2_) REP4(FFMA2_), (unsigned)(p0 ^ p1 ^ p2 ^ p3))
+
+#define IMADW_DECL U_DECL; unsigned long long w0 = u0, w1 = u1, w2 = u2, w3 = u3, w4 = u4, w5 = u5, w6 = u6, w7 = u7
+#define IMADW_(i) asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(w##i) : "r"(ka));
+BENCH_KERNEL(k_imad_wide, IMADW_DECL, REP8(IMADW_) REP8(IMADW_), (unsigned)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7))
+
+#define IMAD_(i) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(u##i) : "r"(ka), "r"(kb));
+BENCH_KERNEL(k_imad, U_DECL, REP8(IMAD_) REP8(IMAD_), U_SINK)
+
+#define IMADHI_(i) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(u##i) : "r"(ka), "r"(kb));
+BENCH_KERNEL(k_imad_hi, U_DECL, REP8(IMADHI_) REP8(IMADHI_), U_SINK)
+
+#define LOP3_(i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u##i) : "r"(ka), "r"(kb));
+BENCH_KERNEL(k_lop3, U_DECL, REP8(LOP3_) REP8(LOP3_), U_SINK)
+
+#define IADD3_(i) asm volatile("add.u32 %0, %0, %1;" : "+r"(u##i) : "r"(ka));
+BENCH_KERNEL(k_iadd, U_DECL, REP8(IADD3_) REP8(IADD3_), U_SINK)
+
+#define SHF_(i) asm volatile("shf.r.wrap.b32 %0, %0, %1, 9;" : "+r"(u##i) : "r"(ka));
+BENCH_KERNEL(k_shf, U_DECL, REP8(SHF_) REP8(SHF_), U_SINK)
+
+#define PRMT_(i) asm volatile("prmt.b32 %0, %0, %1, 0x7610;" : "+r"(u##i) : "r"(ka));
+BENCH_KERNEL(k_prmt, U_DECL, REP8(PRMT_) REP8(PRMT_), U_SINK)
+
+#define ISETP_(i) asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; @p add.u32 %0, %0, 1; }" : "+r"(u##i) : "r"(ka));
+BENCH_KERNEL(k_isetp_padd, U_DECL, REP8(ISETP_) REP8(ISETP_), U_SINK)
+
+#define I2FP_(i) asm volatile("{ .reg .f32 t; cvt.rn.f32.u32 t, %0; mov.b32 %0, t; }" : "+r"(u##i));
+BENCH_KERNEL(k_i2fp, U_DECL, REP8(I2FP_) REP8(I2FP_), U_SINK)
+
+#define F2I_(i) asm volatile("{ .reg .u32 t; cvt.rzi.u32.f32 t, %0; mov.b32 %0, t; }" : "+f"(f##i));
+BENCH_KERNEL(k_f2i, F_DECL, REP8(F2I_) REP8(F2I_), F_SINK)
+
+#define LG2_(i) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(f##i));
+BENCH_KERNEL(k_mufu_lg2, F_DECL, REP8(LG2_) REP8(LG2_), F_SINK)
+#define SQRT_(i) asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(f##i));
+BENCH_KERNEL(k_mufu_sqrt, F_DECL, REP8(SQRT_) REP8(SQRT_), F_SINK)
+#define RSQ_(i) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(f##i));
+BENCH_KERNEL(k_mufu_rsq, F_DECL, REP8(RSQ_) REP8(RSQ_), F_SINK)
+#define SIN_(i) asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(f##i));
+BENCH_KERNEL(k_sin_approx, F_DECL, REP8(SIN_) REP8(SIN_), F_SINK)
+#define EX2_(i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f##i));
+BENCH_KERNEL(k_mufu_ex2, F_DECL, REP8(EX2_) REP8(EX2_), F_SINK)
+
+// mixes: FMA pipe + ALU pipe, FMA pipe + MUFU
+#define MIX_DECL F_DECL; U_DECL
+#define MIX_FL_(i) FFMA_(i) LOP3_(i)
+BENCH_KERNEL(k_mix_ffma_lop3, MIX_DECL, REP8(MIX_FL_), F_SINK ^ U_SINK)
+#define MIX_IL_DECL IMADW_DECL
+#define MIX_IL_(i) IMADW_(i) LOP3_(i)
+BENCH_KERNEL(k_mix_imadw_lop3, MIX_IL_DECL, REP8(MIX_IL_), U_SINK ^ (unsigned)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7))
+#define MIX_FI_DECL F_DECL; IMADW_DECL
+#define MIX_FI_(i) FFMA_(i) IMADW_(i)
+BENCH_KERNEL(k_mix_ffma_imadw, MIX_FI_DECL, REP8(MIX_FI_), F_SINK ^ (unsigned)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7))
+// 7 FFMA : 1 MUFU
+#define MIX_FM_(i) FFMA_(i) FFMA_(i)
+BENCH_KERNEL(k_mix_14ffma_2mufu, F_DECL, REP8(MIX_FM_) LG2_(0) SQRT_(1), F_SINK)
+// FFMA : LOP3 : MUFU = 8 : 8 : 2 (roughly the walk's shape)
+BENCH_KERNEL(k_mix_8ffma_8lop3_2mufu, MIX_DECL, REP8(MIX_FL_) LG2_(0) SQRT_(1), F_SINK ^ U_SINK)
+
+// whole Philox4x32-10 blocks, 2 independent counters per thread
+__device__ __forceinline__ void philox10(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0, unsigned k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ (k0 + r * 0x9E3779B9u);
+        const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ (k1 + r * 0xBB67AE85u);
+        c1 = (unsigned)p1; c3 = (unsigned)p0; c0 = n0; c2 = n2;
+    }
+}
+__global__ void __launch_bounds__(kBlock) k_philox10(Out* out, unsigned seed)
+{
+    unsigned a0 = threadIdx.x, a1 = seed, a2 = 1, a3 = 0, b0 = threadIdx.x + 7777, b1 = seed, b2 = 2, b3 = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters; ++it) {
+        philox10(a0, a1, a2, a3, seed, seed ^ 0x55u);
+        philox10(b0, b1, b2, b3, seed, seed ^ 0x55u);
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x].cycles = t1 - t0;
+    if ((a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3) == 0x12345u) out[blockIdx.x].sink = 1;
+}
+
+// shared-memory atomics: MODE 0 conflict-free (bank = lane), 1 random over `nb` bins,
+// 2 one address per warp-instruction (all 32 lanes collide), 3 random, 20 % of lanes on one hot bin
+template <int MODE, bool RETURN>
+__global__ void __launch_bounds__(kBlock) k_atoms(Out* out, unsigned seed, int nb)
+{
+    extern __shared__ unsigned bins[];
+    for (int i = threadIdx.x; i < nb + 32; i += kBlock) bins[i] = 0;
+    unsigned s = seed * 2654435761u + (blockIdx.x * kBlock + threadIdx.x) * 40503u + 1u;
+    unsigned acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s = s * 1664525u + 1013904223u;
+            unsigned idx;
+            if (MODE == 0) idx = (threadIdx.x & 31) + ((s >> 27) & ~31u) % (unsigned)(nb > 32 ? nb - 32 : 1);
+            else if (MODE == 1) idx = __umulhi(s, (unsigned)nb);
+            else if (MODE == 2) idx = (unsigned)(it & 63);
+            else idx = (s & 0xF0000000u) < 0x30000000u ? (unsigned)nb - 1 : __umulhi(s, (unsigned)nb);
+            if (RETURN) acc += atomicAdd(&bins[idx], s >> 12);
+            else asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&bins[idx])), "r"(s >> 12) : "memory");
+        }
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x].cycles = t1 - t0;
+    if ((acc ^ bins[threadIdx.x % nb]) == 0x12345u) out[blockIdx.x].sink = 1;
+}
+// same address arithmetic without the atomic, to subtract its cost
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_atoms_baseline(Out* out, unsigned seed, int nb)
+{
+    unsigned s = seed * 2654435761u + (blockIdx.x * kBlock + threadIdx.x) * 40503u + 1u;
+    unsigned acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s = s * 1664525u + 1013904223u;
+            unsigned idx = (MODE == 1) ? __umulhi(s, (unsigned)nb) : (unsigned)(it & 63);
+            acc += idx ^ (s >> 12);
+        }
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x].cycles = t1 - t0;
+    if (acc == 0x12345u) out[blockIdx.x].sink = 1;
+}
+
+struct Result {
+    double cycles, ms;
+};
+
+template <typename F>
+Result run(F launch, Out* d_out, int grid)
+{
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    std::vector<Out> h(grid);
+    Result best{1e300, 0};
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0));
+        launch();
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        CK(cudaMemcpy(h.data(), d_out, grid * sizeof(Out), cudaMemcpyDeviceToHost));
+        double c = 0;
+        for (auto& o : h) c += (double)o.cycles;
+        c /= grid;
+        if (rep > 0 && c < best.cycles) best = {c, ms};
+    }
+    return best;
+}
+
+int main(int argc, char** argv)
+{
+    int dev = 0;
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    const int sms = prop.multiProcessorCount;
+    int blocks_per_sm = argc > 1 ? atoi(argv[1]) : 4;   // 4 x 256 threads = 32 warps / SM
+    const int grid = sms * blocks_per_sm;
+    Out* d_out;
+    CK(cudaMalloc(&d_out, grid * sizeof(Out)));
+    CK(cudaMemset(d_out, 0, grid * sizeof(Out)));
+    const double warps_per_sm = blocks_per_sm * kBlock / 32.0;
+    printf("{\"device\": \"%s\", \"sms\": %d, \"cc\": \"%d.%d\", \"warps_per_sm\": %.0f, \"clock_rate_khz\": %d}\n",
+           prop.name, sms, prop.major, prop.minor, warps_per_sm, prop.clockRate);
+
+#define REPORT(NAME, INST_PER_ITER, LAUNCH)                                                        \
+    do {                                                                                           \
+        Result r = run([&] { LAUNCH; }, d_out, grid);                                              \
+        const double winst = (double)(INST_PER_ITER) * kIters * warps_per_sm;                      \
+        printf("{\"test\": \"%s\", \"warp_inst_per_clk_per_sm\": %.3f, \"lanes_per_clk_per_sm\": %.1f, " \
+               "\"cycles\": %.0f, \"ms\": %.4f, \"sm_mhz\": %.0f}\n",                             \
+               NAME, winst / r.cycles, 32.0 * winst / r.cycles, r.cycles, r.ms, r.cycles / r.ms * 1e-3); \
+        fflush(stdout);                                                                            \
+    } while (0)
+
+#define SIMPLE(K, N) REPORT(#K, N, (K<<<grid, kBlock>>>(d_out, 1u)))
+    SIMPLE(k_ffma, 16);
+    SIMPLE(k_fmul, 16);
+    SIMPLE(k_fadd, 16);
+    SIMPLE(k_ffma2, 16);
+    SIMPLE(k_imad_wide, 16);
+    SIMPLE(k_imad, 16);
+    SIMPLE(k_imad_hi, 16);
+    SIMPLE(k_lop3, 16);
+    SIMPLE(k_iadd, 16);
+    SIMPLE(k_shf, 16);
+    SIMPLE(k_prmt, 16);
+    SIMPLE(k_isetp_padd, 32);
+    SIMPLE(k_i2fp, 16);
+    SIMPLE(k_f2i, 16);
+    SIMPLE(k_mufu_lg2, 16);
+    SIMPLE(k_mufu_sqrt, 16);
+    SIMPLE(k_mufu_rsq, 16);
+    SIMPLE(k_sin_approx, 32);   // FMUL.RZ + MUFU.SIN
+    SIMPLE(k_mufu_ex2, 16);
+    SIMPLE(k_mix_ffma_lop3, 16);
+    SIMPLE(k_mix_imadw_lop3, 16);
+    SIMPLE(k_mix_ffma_imadw, 16);
+    SIMPLE(k_mix_14ffma_2mufu, 18);
+    SIMPLE(k_mix_8ffma_8lop3_2mufu, 18);
+    SIMPLE(k_philox10, 80);     // 2 x (20 IMAD.WIDE + 20 LOP3), key schedule folded by ptxas
+
+    const int nbs[] = {101, 1024, 8192};
+    for (int nb : nbs) {
+        const size_t sm = (nb + 32) * sizeof(unsigned);
+        char name[96];
+        snprintf(name, sizeof name, "atoms_red_conflictfree_nb%d", nb);
+        REPORT(name, 8, (k_atoms<0, false><<<grid, kBlock, sm>>>(d_out, 1u, nb)));
+        snprintf(name, sizeof name, "atoms_red_random_nb%d", nb);
+        REPORT(name, 8, (k_atoms<1, false><<<grid, kBlock, sm>>>(d_out, 1u, nb)));
+        snprintf(name, sizeof name, "atoms_ret_random_nb%d", nb);
+        REPORT(name, 8, (k_atoms<1, true><<<grid, kBlock, sm>>>(d_out, 1u, nb)));
+        snprintf(name, sizeof name, "atoms_red_sameaddr_nb%d", nb);
+        REPORT(name, 8, (k_atoms<2, false><<<grid, kBlock, sm>>>(d_out, 1u, nb)));
+        snprintf(name, sizeof name, "atoms_red_random_hot20_nb%d", nb);
+        REPORT(name, 8, (k_atoms<3, false><<<grid, kBlock, sm>>>(d_out, 1u, nb)));
+        snprintf(name, sizeof name, "atoms_baseline_random_nb%d", nb);
+        REPORT(name, 8, (k_atoms_baseline<1><<<grid, kBlock>>>(d_out, 1u, nb)));
+    }
+    REPORT("atoms_baseline_sameaddr", 8, (k_atoms_baseline<2><<<grid, kBlock>>>(d_out, 1u, 101)));
+    CK(cudaFree(d_out));
+    return 0;
+}

@@ -1,0 +1,560 @@
+// tmc_api.cu — C-ABI entry points of libtinymc_b200.so (declared in include/tiny_mc_b200.h).
+//
+// Host side of the drop-in boundary: turns the reference's call site
+//     for (i = 0; i < PHOTONS; ++i) photon(heat, heat2);        (reference tiny_mc.c:47-49)
+// into one launch per GPU of tmc::photon_walk_kernel, one reduce of the 2*SHELLS+4 tally
+// words (NCCL over NVLink when more than one GPU is driven by this process), one small D2H
+// copy, and a += into the caller's float arrays (reference photon.c:30-31 semantics).
+//
+// No CPU fallback: without a usable sm_100 device every compute entry point fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and enums only; the library itself is dlopen()ed on first multi-GPU init
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tiny_mc_b200.h"
+#include "walk_kernel.cuh"
+
+namespace {
+
+using tmc::WalkArgs;
+
+struct Plan {
+    float albedo;
+    float shells_per_mfp;
+    tmc_scales sc;
+    uint32_t weight_one;
+    uint32_t heat2_half;
+};
+
+struct Device {
+    int id = -1;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long* d_buf = nullptr;   // u64[2*shells+4]
+    size_t buf_words = 0;
+    ncclComm_t comm = nullptr;
+};
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+struct Options {
+    int philox_rounds = 10;
+    int block_threads = 0;   // 0 = auto
+    int blocks_per_sm = 0;   // 0 = occupancy
+    int flush_iters = 0;     // 0 = auto
+    int nccl_reduce = 1;
+};
+
+struct Lib {
+    bool inited = false;
+    std::vector<Device> devs;
+    NcclApi nccl;
+    Options opt;
+    std::string err = "";
+    tmc_run_info info{};
+    unsigned long long* h_pinned = nullptr;
+    size_t h_words = 0;
+} g;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g.err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(TMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define NCCL_TRY(expr)                                                                              \
+    do {                                                                                            \
+        ncclResult_t r_ = (expr);                                                                   \
+        if (r_ != ncclSuccess)                                                                      \
+            return fail(TMC_ERR_NCCL, "%s failed: %s", #expr, g.nccl.GetErrorString ? g.nccl.GetErrorString(r_) : "?"); \
+    } while (0)
+
+uint32_t ceil_log2_u64(uint64_t v)
+{
+    uint32_t b = 0;
+    while (b < 63 && (1ull << b) < v) ++b;
+    return b;
+}
+
+// Optical constants (reference photon.c:8-9) and the fixed-point plan.
+int make_plan(const tmc_params* p, Plan* pl)
+{
+    if (!p) return fail(TMC_ERR_BAD_ARG, "params is NULL");
+    if (p->shells < 1u || p->shells > (1u << 22)) return fail(TMC_ERR_BAD_ARG, "SHELLS=%u out of range [1, 2^22]", p->shells);
+    if (!(p->mu_a > 0.0f) || !(p->mu_s >= 0.0f) || !(p->microns_per_shell > 0.0f))
+        return fail(TMC_ERR_BAD_ARG, "need MU_A > 0, MU_S >= 0, MICRONS_PER_SHELL > 0");
+    pl->albedo = p->mu_s / (p->mu_s + p->mu_a);
+    pl->shells_per_mfp = static_cast<float>(1e4 / static_cast<double>(p->microns_per_shell) /
+                                            static_cast<double>(p->mu_a + p->mu_s));
+    const double absorb = 1.0 - static_cast<double>(pl->albedo);
+    int hs = 21 - static_cast<int>(std::ceil(std::log2(absorb)));
+    if (hs > 30) hs = 30;
+    if (hs < 16) hs = 16;
+    pl->sc.heat_shift = static_cast<uint32_t>(hs);
+    pl->weight_one = 1u << hs;
+    double q = std::floor(absorb * 4294967296.0 + 0.5);
+    if (q > 4294967295.0) q = 4294967295.0;
+    if (q < 1.0) q = 1.0;
+    pl->sc.absorb_q32 = static_cast<uint32_t>(q);
+    const uint64_t dep_max = (static_cast<uint64_t>(pl->weight_one) * pl->sc.absorb_q32) >> 32;
+    const uint32_t bits = ceil_log2_u64(dep_max + 1);
+    pl->sc.heat2_rshift = (2 * bits > 22) ? 2 * bits - 22 : 0;
+    pl->heat2_half = pl->sc.heat2_rshift ? (1u << (pl->sc.heat2_rshift - 1)) : 0u;
+    pl->sc.roulette_thr = static_cast<uint32_t>(std::floor(0.001 * pl->weight_one + 0.5));
+    return TMC_OK;
+}
+
+using KernelFn = void (*)(const WalkArgs);
+
+template <int ROUNDS>
+KernelFn kernel_for_block(int block)
+{
+    switch (block) {
+    case 128: return tmc::photon_walk_kernel<ROUNDS, 128, 8>;
+    case 256: return tmc::photon_walk_kernel<ROUNDS, 256, 4>;
+    case 512: return tmc::photon_walk_kernel<ROUNDS, 512, 2>;
+    case 1024: return tmc::photon_walk_kernel<ROUNDS, 1024, 1>;
+    default: return nullptr;
+    }
+}
+
+KernelFn pick_kernel(int rounds, int block)
+{
+    switch (rounds) {
+    case 7: return kernel_for_block<7>(block);
+    case 8: return kernel_for_block<8>(block);
+    case 9: return kernel_for_block<9>(block);
+    case 10: return kernel_for_block<10>(block);
+    default: return nullptr;
+    }
+}
+
+struct LaunchCfg {
+    KernelFn fn;
+    int block;
+    int grid;
+    size_t smem;
+    uint32_t flush_iters;
+};
+
+int configure_launch(const tmc_params* p, int device_sms, uint64_t count, uint32_t flush_override, LaunchCfg* cfg)
+{
+    const size_t smem = static_cast<size_t>(2) * p->shells * sizeof(uint32_t);
+    if (smem > 227u * 1024u)
+        return fail(TMC_ERR_BAD_ARG, "SHELLS=%u needs %zu B of shared memory per block (> 227 KB)", p->shells, smem);
+    int block = g.opt.block_threads;
+    if (block == 0) block = (smem > 56u * 1024u) ? 1024 : 256;
+    KernelFn fn = pick_kernel(g.opt.philox_rounds, block);
+    if (!fn) return fail(TMC_ERR_BAD_ARG, "no kernel for philox_rounds=%d block_threads=%d", g.opt.philox_rounds, block);
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
+    if (per_sm < 1) return fail(TMC_ERR_CUDA, "kernel does not fit on an SM (block=%d smem=%zu)", block, smem);
+    if (g.opt.blocks_per_sm > 0 && g.opt.blocks_per_sm < per_sm) per_sm = g.opt.blocks_per_sm;
+    uint64_t grid = static_cast<uint64_t>(device_sms) * per_sm;
+    const uint64_t needed = (count + block - 1) / block;
+    if (needed < grid) grid = needed ? needed : 1;
+    uint32_t flush = flush_override ? flush_override : static_cast<uint32_t>(g.opt.flush_iters);
+    if (flush == 0) {
+        // Hottest regular bin receives <~1.5 % of a block's events; with 2^21-scale deposits a
+        // 32-iteration interval leaves > 10x head-room below the 2^31 check.
+        // Wide grids spread the events over more bins, so the interval can grow with SHELLS.
+        flush = 32u;
+        if (p->shells > 512u) flush = 32u * (p->shells / 512u);
+        if (flush > 512u) flush = 512u;
+        flush = flush * 256u / static_cast<uint32_t>(block);
+        if (flush < 8u) flush = 8u;
+    }
+    if (flush > 1000u) flush = 1000u;   // per-thread overflow-bin registers: 2*flush*2^21 < 2^32
+    cfg->fn = fn;
+    cfg->block = block;
+    cfg->grid = static_cast<int>(grid);
+    cfg->smem = smem;
+    cfg->flush_iters = flush;
+    return TMC_OK;
+}
+
+int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t first, uint64_t count,
+                 const LaunchCfg& cfg, unsigned long long* d_buf, cudaStream_t stream)
+{
+    WalkArgs a;
+    tmc::philox_expand_key(seed, &a.keys);
+    a.first = first;
+    a.count = count;
+    a.tallies = d_buf;
+    a.counters = d_buf + 2ull * p->shells;
+    a.shells_per_mfp = pl.shells_per_mfp;
+    a.shells = p->shells;
+    a.last_bits = tmc::kMagicBits + p->shells - 1u;
+    a.weight_one = pl.weight_one;
+    a.absorb_q32 = pl.sc.absorb_q32;
+    a.heat2_rshift = pl.sc.heat2_rshift;
+    a.heat2_half = pl.heat2_half;
+    a.roulette_thr = pl.sc.roulette_thr;
+    a.flush_iters = cfg.flush_iters;
+    void* params[] = { &a };
+    CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(cfg.fn), dim3(cfg.grid), dim3(cfg.block), params, cfg.smem, stream));
+    return TMC_OK;
+}
+
+int check_device_arch(int dev)
+{
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(TMC_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", dev, prop.name, prop.major, prop.minor);
+    return TMC_OK;
+}
+
+int load_nccl()
+{
+    if (g.nccl.handle) return TMC_OK;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char* n : names) {
+        g.nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g.nccl.handle) break;
+    }
+    if (!g.nccl.handle) return fail(TMC_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define LOAD(sym)                                                                     \
+    g.nccl.sym = reinterpret_cast<decltype(g.nccl.sym)>(dlsym(g.nccl.handle, "nccl" #sym)); \
+    if (!g.nccl.sym) return fail(TMC_ERR_NCCL, "libnccl lacks nccl" #sym)
+    LOAD(CommInitAll);
+    LOAD(CommDestroy);
+    LOAD(Reduce);
+    LOAD(GroupStart);
+    LOAD(GroupEnd);
+    LOAD(GetErrorString);
+#undef LOAD
+    return TMC_OK;
+}
+
+int ensure_buffers(size_t words)
+{
+    for (Device& d : g.devs) {
+        if (d.buf_words >= words) continue;
+        CUDA_TRY(cudaSetDevice(d.id));
+        if (d.d_buf) CUDA_TRY(cudaFree(d.d_buf));
+        d.d_buf = nullptr;
+        CUDA_TRY(cudaMalloc(&d.d_buf, words * sizeof(unsigned long long)));
+        d.buf_words = words;
+    }
+    const size_t host_words = words * g.devs.size();
+    if (g.h_words < host_words) {
+        if (g.h_pinned) CUDA_TRY(cudaFreeHost(g.h_pinned));
+        g.h_pinned = nullptr;
+        CUDA_TRY(cudaMallocHost(&g.h_pinned, host_words * sizeof(unsigned long long)));
+        g.h_words = host_words;
+    }
+    return TMC_OK;
+}
+
+// One pass over [first, first+count): launch on every device, reduce, copy back.
+// On success `out` (host, 2*shells+4 words) holds the summed buffer.
+int run_range(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t first, uint64_t count,
+              uint32_t flush_override, std::vector<unsigned long long>& out, double* kernel_ms)
+{
+    const size_t words = 2ull * p->shells + 4ull;
+    const int ng = static_cast<int>(g.devs.size());
+    int rc = ensure_buffers(words);
+    if (rc) return rc;
+    LaunchCfg cfg0{};
+    for (int i = 0; i < ng; ++i) {
+        Device& d = g.devs[i];
+        const uint64_t lo = first + count / ng * i + (static_cast<uint64_t>(i) < count % ng ? i : count % ng);
+        const uint64_t n = count / ng + (static_cast<uint64_t>(i) < count % ng ? 1 : 0);
+        CUDA_TRY(cudaSetDevice(d.id));
+        LaunchCfg cfg{};
+        rc = configure_launch(p, d.sms, n, flush_override, &cfg);
+        if (rc) return rc;
+        if (i == 0) cfg0 = cfg;
+        CUDA_TRY(cudaMemsetAsync(d.d_buf, 0, words * sizeof(unsigned long long), d.stream));
+        CUDA_TRY(cudaEventRecord(d.ev0, d.stream));
+        if (n > 0) {
+            rc = enqueue_walk(p, pl, seed, lo, n, cfg, d.d_buf, d.stream);
+            if (rc) return rc;
+            g.info.gpu_launches += 1;
+        }
+        CUDA_TRY(cudaEventRecord(d.ev1, d.stream));
+    }
+    const bool use_nccl = ng > 1 && g.opt.nccl_reduce && g.devs[0].comm;
+    if (use_nccl) {
+        // The single collective of the path: sum heat|heat2|counters (u64, exact) onto device 0.
+        NCCL_TRY(g.nccl.GroupStart());
+        for (int i = 0; i < ng; ++i) {
+            Device& d = g.devs[i];
+            NCCL_TRY(g.nccl.Reduce(d.d_buf, d.d_buf, words, ncclUint64, ncclSum, 0, d.comm, d.stream));
+        }
+        NCCL_TRY(g.nccl.GroupEnd());
+    }
+    const int n_read = use_nccl ? 1 : ng;
+    for (int i = 0; i < n_read; ++i) {
+        Device& d = g.devs[i];
+        CUDA_TRY(cudaSetDevice(d.id));
+        CUDA_TRY(cudaMemcpyAsync(g.h_pinned + i * words, d.d_buf, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+    }
+    double worst = 0.0;
+    for (int i = 0; i < ng; ++i) {
+        Device& d = g.devs[i];
+        CUDA_TRY(cudaSetDevice(d.id));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        if (ms > worst) worst = ms;
+    }
+    out.assign(words, 0ull);
+    for (int i = 0; i < n_read; ++i)
+        for (size_t w = 0; w < words; ++w) out[w] += g.h_pinned[i * words + w];
+    *kernel_ms += worst;
+    g.info.blocks_per_gpu = static_cast<uint32_t>(cfg0.grid);
+    g.info.threads_per_block = static_cast<uint32_t>(cfg0.block);
+    g.info.flush_iters = cfg0.flush_iters;
+    g.info.smem_bytes = static_cast<uint32_t>(cfg0.smem);
+    return TMC_OK;
+}
+
+// Whole call: chunk so that no u64 tally can overflow, retry with a shorter drain interval if
+// the 2^31 range check fired, add the exact totals into the caller's u64 arrays.
+int run_fx(const tmc_params* p, uint64_t seed, uint64_t first, uint64_t n, uint64_t* heat_fx, uint64_t* heat2_fx)
+{
+    if (!g.inited) return fail(TMC_ERR_NO_DEVICE, "tmc_init has not been called (or found no sm_100 GPU)");
+    if (!heat_fx || !heat2_fx) return fail(TMC_ERR_BAD_ARG, "tally pointer is NULL");
+    Plan pl;
+    int rc = make_plan(p, &pl);
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    g.info = tmc_run_info{};
+    g.info.n_gpus = static_cast<uint32_t>(g.devs.size());
+    g.info.philox_rounds = static_cast<uint32_t>(g.opt.philox_rounds);
+    double kernel_ms = 0.0;
+    const uint64_t max_chunk = 1ull << (62 - pl.sc.heat_shift);   // chunk * 2^heat_shift < 2^62
+    std::vector<unsigned long long> sum;
+    uint64_t done = 0;
+    while (done < n) {
+        const uint64_t todo = (n - done < max_chunk) ? n - done : max_chunk;
+        uint32_t flush_override = 0;
+        for (int attempt = 0;; ++attempt) {
+            rc = run_range(p, pl, seed, first + done, todo, flush_override, sum, &kernel_ms);
+            if (rc) return rc;
+            if (sum[2ull * p->shells + 2] == 0ull) break;
+            if (attempt == 3 || g.info.flush_iters <= 1u)
+                return fail(TMC_ERR_TALLY_RANGE, "a shared tally exceeded 2^31 within %u iterations", g.info.flush_iters);
+            flush_override = g.info.flush_iters / 8u ? g.info.flush_iters / 8u : 1u;
+            g.info.retries += 1;
+        }
+        for (uint32_t s = 0; s < p->shells; ++s) {
+            heat_fx[s] += sum[s];
+            heat2_fx[s] += sum[p->shells + s];
+        }
+        g.info.events += sum[2ull * p->shells];
+        g.info.photons += sum[2ull * p->shells + 1];
+        done += todo;
+    }
+    g.info.kernel_ms = kernel_ms;
+    g.info.call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (g.info.photons != n) return fail(TMC_ERR_CUDA, "internal: simulated %llu photons, expected %llu", (unsigned long long)g.info.photons, (unsigned long long)n);
+    return TMC_OK;
+}
+
+void accumulate_float(const tmc_params* p, const Plan& pl, const uint64_t* heat_fx, const uint64_t* heat2_fx,
+                      float* heats, float* heats_squared)
+{
+    const double s1 = std::ldexp(1.0, -static_cast<int>(pl.sc.heat_shift));
+    const double s2 = std::ldexp(1.0, static_cast<int>(pl.sc.heat2_rshift) - 2 * static_cast<int>(pl.sc.heat_shift));
+    for (uint32_t s = 0; s < p->shells; ++s) {
+        heats[s] += static_cast<float>(static_cast<double>(heat_fx[s]) * s1);
+        heats_squared[s] += static_cast<float>(static_cast<double>(heat2_fx[s]) * s2);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tmc_abi_version(void) { return TMC_ABI_VERSION; }
+const char* tmc_version(void) { return "tiny_mc_b200 0.1 (sm_100a, stream tmc-stream-1)"; }
+const char* tmc_last_error(void) { return g.err.c_str(); }
+int tmc_device_count(void) { return g.inited ? static_cast<int>(g.devs.size()) : 0; }
+
+int tmc_finalize(void)
+{
+    for (Device& d : g.devs) {
+        cudaSetDevice(d.id);
+        if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
+        if (d.d_buf) cudaFree(d.d_buf);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    g.devs.clear();
+    if (g.h_pinned) cudaFreeHost(g.h_pinned);
+    g.h_pinned = nullptr;
+    g.h_words = 0;
+    g.inited = false;
+    return TMC_OK;
+}
+
+int tmc_init(int n_gpus)
+{
+    if (g.inited) tmc_finalize();
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible < 1)
+        return fail(TMC_ERR_NO_DEVICE, "no CUDA device: %s (this library has no CPU fallback)", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (n_gpus <= 0) n_gpus = visible;
+    if (n_gpus > visible) return fail(TMC_ERR_NO_DEVICE, "asked for %d GPUs, %d visible", n_gpus, visible);
+    g.devs.resize(n_gpus);
+    for (int i = 0; i < n_gpus; ++i) {
+        Device& d = g.devs[i];
+        d = Device{};
+        d.id = i;
+        int rc = check_device_arch(i);
+        if (rc) { g.devs.clear(); return rc; }
+        CUDA_TRY(cudaSetDevice(i));
+        CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, i));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&d.ev0));
+        CUDA_TRY(cudaEventCreate(&d.ev1));
+    }
+    if (n_gpus > 1 && g.opt.nccl_reduce) {
+        int rc = load_nccl();
+        if (rc) return rc;
+        std::vector<ncclComm_t> comms(n_gpus);
+        std::vector<int> ids(n_gpus);
+        for (int i = 0; i < n_gpus; ++i) ids[i] = i;
+        NCCL_TRY(g.nccl.CommInitAll(comms.data(), n_gpus, ids.data()));
+        for (int i = 0; i < n_gpus; ++i) g.devs[i].comm = comms[i];
+    }
+    g.inited = true;
+    return TMC_OK;
+}
+
+int tmc_set_option(const char* name, long long value)
+{
+    if (!name) return fail(TMC_ERR_BAD_ARG, "option name is NULL");
+    const std::string n(name);
+    if (n == "philox_rounds") {
+        if (value == 0) value = 10;
+        if (value < 7 || value > 10) return fail(TMC_ERR_BAD_ARG, "philox_rounds must be 7..10");
+        g.opt.philox_rounds = static_cast<int>(value);
+    } else if (n == "block_threads") {
+        if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024)
+            return fail(TMC_ERR_BAD_ARG, "block_threads must be 0, 128, 256, 512 or 1024");
+        g.opt.block_threads = static_cast<int>(value);
+    } else if (n == "blocks_per_sm") {
+        if (value < 0 || value > 32) return fail(TMC_ERR_BAD_ARG, "blocks_per_sm must be 0..32");
+        g.opt.blocks_per_sm = static_cast<int>(value);
+    } else if (n == "flush_iters") {
+        if (value < 0 || value > 1000) return fail(TMC_ERR_BAD_ARG, "flush_iters must be 0..1000");
+        g.opt.flush_iters = static_cast<int>(value);
+    } else if (n == "nccl_reduce") {
+        g.opt.nccl_reduce = value ? 1 : 0;
+    } else {
+        return fail(TMC_ERR_BAD_ARG, "unknown option '%s'", name);
+    }
+    return TMC_OK;
+}
+
+int tmc_fx_scales(const tmc_params* p, tmc_scales* out)
+{
+    if (!out) return fail(TMC_ERR_BAD_ARG, "out is NULL");
+    Plan pl;
+    int rc = make_plan(p, &pl);
+    if (rc) return rc;
+    *out = pl.sc;
+    return TMC_OK;
+}
+
+int tmc_fx_accumulate(const tmc_params* p, const uint64_t* heat_fx, const uint64_t* heat2_fx, float* heats, float* heats_squared)
+{
+    if (!heat_fx || !heat2_fx || !heats || !heats_squared) return fail(TMC_ERR_BAD_ARG, "NULL pointer");
+    Plan pl;
+    int rc = make_plan(p, &pl);
+    if (rc) return rc;
+    accumulate_float(p, pl, heat_fx, heat2_fx, heats, heats_squared);
+    return TMC_OK;
+}
+
+int tmc_photons_fx(const tmc_params* p, uint64_t seed, uint64_t first_photon, uint64_t n_photons, uint64_t* heat_fx, uint64_t* heat2_fx)
+{
+    return run_fx(p, seed, first_photon, n_photons, heat_fx, heat2_fx);
+}
+
+int tmc_photons(const tmc_params* p, uint64_t seed, uint64_t first_photon, uint64_t n_photons, float* heats, float* heats_squared)
+{
+    if (!heats || !heats_squared) return fail(TMC_ERR_BAD_ARG, "tally pointer is NULL");
+    Plan pl;
+    int rc = make_plan(p, &pl);
+    if (rc) return rc;
+    std::vector<uint64_t> fx(2ull * p->shells, 0ull);
+    rc = run_fx(p, seed, first_photon, n_photons, fx.data(), fx.data() + p->shells);
+    if (rc) return rc;
+    accumulate_float(p, pl, fx.data(), fx.data() + p->shells, heats, heats_squared);
+    return TMC_OK;
+}
+
+int tmc_photons_device(const tmc_params* p, uint64_t seed, uint64_t first_photon, uint64_t n_photons, int device, void* d_tallies, void* cuda_stream)
+{
+    if (!d_tallies) return fail(TMC_ERR_BAD_ARG, "d_tallies is NULL");
+    Plan pl;
+    int rc = make_plan(p, &pl);
+    if (rc) return rc;
+    if (n_photons > (1ull << (62 - pl.sc.heat_shift)))
+        return fail(TMC_ERR_BAD_ARG, "n_photons too large for one device call with heat_shift=%u; split the range", pl.sc.heat_shift);
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || device < 0 || device >= visible)
+        return fail(TMC_ERR_NO_DEVICE, "CUDA device %d not available (no CPU fallback)", device);
+    rc = check_device_arch(device);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (n_photons == 0) return TMC_OK;
+    LaunchCfg cfg{};
+    rc = configure_launch(p, sms, n_photons, 0, &cfg);
+    if (rc) return rc;
+    g.info.blocks_per_gpu = static_cast<uint32_t>(cfg.grid);
+    g.info.threads_per_block = static_cast<uint32_t>(cfg.block);
+    g.info.flush_iters = cfg.flush_iters;
+    g.info.smem_bytes = static_cast<uint32_t>(cfg.smem);
+    g.info.philox_rounds = static_cast<uint32_t>(g.opt.philox_rounds);
+    return enqueue_walk(p, pl, seed, first_photon, n_photons, cfg, static_cast<unsigned long long*>(d_tallies), static_cast<cudaStream_t>(cuda_stream));
+}
+
+int tmc_last_run_info(tmc_run_info* out)
+{
+    if (!out) return fail(TMC_ERR_BAD_ARG, "out is NULL");
+    *out = g.info;
+    return TMC_OK;
+}
+
+}  // extern "C"
