@@ -2,16 +2,20 @@
 import numpy as np
 
 
-def batch_means_z(a_batches, a_n, b_batches, b_n, min_mean=0.0):
+def batch_means_z(a_batches, a_n, b_batches, b_n, min_mean=0.0, b_use=None):
     """Per-shell z of the difference of per-photon means, sigma from batch means on both sides.
 
     a_batches, b_batches: [B, S] tallies (weight units) of batches of a_n / b_n photons each.
+    b_use: compare against the mean of only the first `b_use` batches of b (a smaller reference
+    sample), while the per-batch variance is still estimated from ALL batches of b so that the
+    statistic keeps its degrees of freedom.
     """
     a = np.asarray(a_batches, np.float64) / a_n
     b = np.asarray(b_batches, np.float64) / b_n
-    ma, mb = a.mean(axis=0), b.mean(axis=0)
+    k = b.shape[0] if b_use is None else int(b_use)
+    ma, mb = a.mean(axis=0), b[:k].mean(axis=0)
     va = a.var(axis=0, ddof=1) / a.shape[0]
-    vb = b.var(axis=0, ddof=1) / b.shape[0]
+    vb = b.var(axis=0, ddof=1) / k
     sd = np.sqrt(va + vb)
     ok = (sd > 0) & (np.maximum(ma, mb) > min_mean)
     z = np.zeros_like(ma)

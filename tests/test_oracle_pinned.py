@@ -144,13 +144,14 @@ def test_replay_agrees_with_reference_walk_on_sound_rng(orc):
 
 
 def test_replay_agrees_with_reference_at_its_shipped_scale(orc):
-    """The literal contract at the scale the reference itself runs (PHOTONS = 32768, params.h:10):
-    against the UNMODIFIED reference on libc rand(), every shell within 4 sigma."""
+    """The literal contract at the scale the reference itself runs (PHOTONS = 32768, params.h:10;
+    here one 65536-photon batch): against the UNMODIFIED reference on libc rand(), every shell
+    within 4 sigma.  (The libc bias above only becomes resolvable beyond ~5e5 photons.)"""
     from stats import batch_means_z
 
     libc = np.load(GOLDEN / "ref_batches_default.npz")
     n_ref = int(libc["photons_per_batch"])
     nb, n = 32, 1 << 15
-    z, ok = batch_means_z(_replay_batches(orc, "default", nb, n), n, libc["heat"][:4], n_ref)
+    z, ok = batch_means_z(_replay_batches(orc, "default", nb, n), n, libc["heat"], n_ref, b_use=1)
     assert ok.sum() == 101
     assert np.abs(z).max() < 4.0, z
