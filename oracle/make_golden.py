@@ -40,6 +40,7 @@ def main():
     assert orc.have_ref(), "run `make -C oracle ref` first"
     GOLD.mkdir(parents=True, exist_ok=True)
 
+    only = set(sys.argv[1:])
     exact = {}
     for name, seed, n in (("default", 1234, 4096), ("highalbedo", 99, 64), ("finegrid", 4321, 4096)):
         r = orc.run_batch(name, seed, n, chunk=0, impl="reference")
@@ -55,24 +56,29 @@ def main():
     out = subprocess.run([str(orc.REF_DIR / "headless_asshipped")], capture_output=True, text=True, check=True).stdout
     (GOLD / "headless_asshipped.txt").write_text(out)
 
-    plans = (("default", 64, 1 << 16), ("highalbedo", 64, 1 << 10), ("finegrid", 64, 1 << 16))
-    for name, nb, n in plans:
+    # chunk = photons per fresh float tally.  High albedo makes ~7150 deposits of
+    # ~1e-3 * w per photon: even 256-photon float chunks lose 1.3e-4 of the weight, so 8 there.
+    plans = (("default", 64, 1 << 16, 256), ("highalbedo", 64, 1 << 10, 8), ("finegrid", 64, 1 << 16, 256))
+    only = set(sys.argv[1:])
+    for name, nb, n, chunk in plans:
+        if only and name not in only:
+            continue
         seeds = [1000 + 7 * b for b in range(nb)]
-        heat, heat2, _, secs, wall = orc.run_batches(name, seeds, n, chunk=256, impl="reference")
+        heat, heat2, _, secs, wall = orc.run_batches(name, seeds, n, chunk=chunk, impl="reference")
         if name == "finegrid":   # 16384 shells x 64 batches is too big to commit: keep 128-shell groups
             heat = heat.reshape(nb, 128, 128).sum(axis=2)
             heat2 = heat2.reshape(nb, 128, 128).sum(axis=2)
         np.savez_compressed(GOLD / f"ref_batches_{name}.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
-                            photons_per_batch=n, chunk=256)
+                            photons_per_batch=n, chunk=chunk)
         print(f"{name}: {nb} x {n} photons, cpu {secs.sum():.1f} s, wall {wall:.1f} s, "
               f"total/photon {heat.sum() / (nb * n):.6f}")
         # the same walk code (photon_port.c, pinned to the reference above) on a sound generator
-        heat, heat2, _, secs, wall = orc.run_batches(name, seeds, n, chunk=256, impl="port", rng="xoshiro")
+        heat, heat2, _, secs, wall = orc.run_batches(name, seeds, n, chunk=chunk, impl="port", rng="xoshiro")
         if name == "finegrid":
             heat = heat.reshape(nb, 128, 128).sum(axis=2)
             heat2 = heat2.reshape(nb, 128, 128).sum(axis=2)
         np.savez_compressed(GOLD / f"port_xoshiro_batches_{name}.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
-                            photons_per_batch=n, chunk=256)
+                            photons_per_batch=n, chunk=chunk)
         print(f"{name} (xoshiro): total/photon {heat.sum() / (nb * n):.6f}")
 
 

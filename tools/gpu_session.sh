@@ -1,0 +1,28 @@
+#!/bin/bash
+# tools/gpu_session.sh — what one gpurun call runs on the B200 box; everything lands in gpurun_out/.
+# usage: gpurun --timeout 1500 -- 'bash tools/gpu_session.sh [tests] [micro] [bench] [ncu] [sweep]'
+set -u
+mkdir -p gpurun_out
+what="${*:-tests micro bench ncu}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
+nproc > gpurun_out/nproc.txt
+for w in $what; do
+case $w in
+smoke)
+  timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
+tests)
+  timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log ;;
+micro)
+  timeout 300 tiny_mc_b200/bin/tmc_microbench > gpurun_out/microbench.jsonl 2> gpurun_out/microbench.err; echo "micro rc=$?" ;;
+bench)
+  timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json
+  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "bench ref rc=$?" ;;
+ncu)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu launches rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:photon_walk -s 1 -c 1 -f -o gpurun_out/prof \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?" ;;
+sweep)
+  timeout 900 python tools/sweep.py > gpurun_out/sweep.jsonl 2> gpurun_out/sweep.err; echo "sweep rc=$?" ;;
+esac
+done
