@@ -81,7 +81,8 @@ const char* tmc_version(void);
 int tmc_abi_version(void);
 
 /* Tunables: "philox_rounds" (7..10, default 10), "block_threads", "blocks_per_sm",
- * "flush_iters", "nccl_reduce" (1 = NCCL, 0 = host-side sum; default 1).  0 restores default. */
+ * "flush_iters", "nccl_reduce" (1 = NCCL, 0 = host-side sum; default 1), "tally_layout"
+ * (0 = auto, 1 = one histogram per block, 2 = one per lane).  0 restores the default.           */
 int tmc_set_option(const char* name, long long value);
 
 /* The batched form of the reference call site tiny_mc.c:47-49:

@@ -1,8 +1,13 @@
 /* oracle/stream_replay.c — TEST INFRASTRUCTURE ONLY (see oracle/README.md).
  *
  * CPU replay of the PRODUCT's random stream and fixed-point tally arithmetic
- * ("tmc-stream-1"), restated independently in scalar C with libm
- * (log2f / sqrtf / sin / cos) standing in for the GPU's MUFU approximations.
+ * ("tmc-stream-2"), restated independently in scalar C with libm
+ * (log2f / sqrtf, cos / sin in double for the azimuth table) standing in for the GPU's MUFU
+ * approximations.
+ *
+ * Stream layout: photon i draws Philox4x32-R(counter = (i_lo, i_hi, block, 0), key = seed).
+ *   block 0 : word 0 = roulette fate word, word 1 = launch direction, words 2-3 = first event;
+ *   block b : words 0-1 = one event (step word, direction word), words 2-3 = the next event.
  *
  * What it pins (tests/test_gpu_parity.py):
  *   - integer-exact: scatter events per photon, roulette fates, every deposit value and
@@ -75,6 +80,22 @@ void orc_fx_plan(const orc_optics* o, orc_fx_scales* s)
 
 typedef union { uint32_t u; float f; } bits32;
 
+/* New isotropic direction from one word (replaces the rejection loop of photon.c:35-43):
+ * cos(theta) uniform from bits 9..31, azimuth index from bits 3..14 into a 4096-entry table of
+ * (float)cos, (float)sin of 2 pi i / 4096 evaluated in double. */
+static void spin_direction(uint32_t wd, float* dx, float* dy, float* dz)
+{
+    bits32 cb;
+    cb.u = (wd >> 9) | 0x3F800000u;                   /* 1 + m * 2^-23 in [1, 2) */
+    const float ct = fmaf(cb.f, 2.0f, -3.0f);         /* exact */
+    const float nct = fmaf(cb.f, -2.0f, 3.0f);        /* exact */
+    const float st = sqrtf(fmaf(ct, nct, 1.0f));
+    const double phi = 6.283185307179586476925 * (double)((wd >> 3) & 4095u) / 4096.0;
+    *dx = ct;
+    *dy = st * (float)cos(phi);
+    *dz = st * (float)sin(phi);
+}
+
 uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n,
                     uint64_t* heat_fx, uint64_t* heat2_fx)
 {
@@ -92,7 +113,7 @@ uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t p = first + i;
         float x = 0.0f, y = 0.0f, z = 0.0f;
-        float dx = 0.0f, dy = 0.0f, dz = 1.0f;
+        float dx = 0.0f, dy = 0.0f, dz = 0.0f;
         uint32_t w = s.weight_one;
         uint32_t fate = 0;
         int alive = 1;
@@ -101,8 +122,9 @@ uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_
             uint32_t r[4];
             orc_philox4x32(rounds, ctr, key, r);
             int slot = 0;
-            if (blk == 0) { /* birth block: word 0 is the roulette fate, slot A is skipped */
+            if (blk == 0) { /* birth block: word 0 = roulette fate, word 1 = isotropic launch direction */
                 fate = r[0];
+                spin_direction(r[1], &dx, &dy, &dz);
                 slot = 1;
             }
             for (; slot < 2 && alive; ++slot) {
@@ -133,15 +155,7 @@ uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_
                         alive = 0;
                     }
                 }
-                /* spin: cos(theta) from the top 23 bits, azimuth from the low 16 bits */
-                bits32 cb;
-                cb.u = (wd >> 9) | 0x3F800000u;
-                const float ct = fmaf(cb.f, 2.0f, -3.0f);
-                const float st = sqrtf(fmaf(-ct, ct, 1.0f));
-                const double phi = 6.283185307179586476925 * (double)(wd & 0xFFFFu) / 65536.0;
-                dx = ct;
-                dy = st * (float)cos(phi);
-                dz = st * (float)sin(phi);
+                spin_direction(wd, &dx, &dy, &dz);
             }
         }
     }

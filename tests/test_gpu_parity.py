@@ -62,6 +62,11 @@ def test_single_photon_and_empty_range(gpu, orc):
     r, r2, ev = orc.replay("default", 5, 12345678901, 1)       # photon index > 2^32: high counter word
     assert gpu.last_run_info().events == ev and int(h.sum()) == int(r.sum())
     assert np.abs(h.astype(np.int64) - r.astype(np.int64)).sum() <= 2 * r.max()
+    # a range that crosses a multiple of 2^32 is cut into two launches (32-bit photon offsets)
+    lo = (1 << 32) - 1000
+    h, h2 = gpu.photons_fx("default", 5, lo, 3000)
+    r, r2, ev = orc.replay("default", 5, lo, 3000)
+    assert gpu.last_run_info().events == ev and int(h.sum()) == int(r.sum()) and gpu.last_run_info().gpu_launches == 2
     h, h2 = gpu.photons_fx("default", 5, 0, 0)
     assert not h.any() and not h2.any() and gpu.last_run_info().photons == 0
 

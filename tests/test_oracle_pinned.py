@@ -119,13 +119,14 @@ def test_libc_rand_biases_the_reference_itself():
 
     libc = np.load(GOLDEN / "ref_batches_default.npz")
     good = np.load(GOLDEN / "port_xoshiro_batches_default.npz")
-    n = int(libc["photons_per_batch"])
-    z, ok = batch_means_z(good["heat"], n, libc["heat"], n)
+    n, n_good = int(libc["photons_per_batch"]), int(good["photons_per_batch"])
+    z, ok = batch_means_z(good["heat"], n_good, libc["heat"], n)
     assert ok.all()
     assert np.abs(z).max() > 4.0
     assert z[5:40].mean() < -0.8 and z[60:].mean() > 2.0        # the systematic shape of the bias
     # ... while two halves of either set agree with each other (the test itself is calibrated)
     for d in (libc, good):
+        n = int(d["photons_per_batch"])
         z0, _ = batch_means_z(d["heat"][:32], n, d["heat"][32:], n)
         assert np.abs(z0).max() < 4.0 and abs(z0.mean()) < 0.5
 

@@ -27,7 +27,7 @@
     } while (0)
 
 constexpr int kBlock = 256;
-constexpr int kIters = 2048;   // outer loop trips
+constexpr int kIters = 16384;  // outer loop trips (long enough that launch latency and clock ramp vanish)
 constexpr int kChains = 8;     // independent dependency chains per thread
 
 struct Out {
@@ -129,6 +129,33 @@ BENCH_KERNEL(k_mix_imadw_lop3, MIX_IL_DECL, REP8(MIX_IL_), U_SINK ^ (unsigned)(w
 #define MIX_FI_DECL F_DECL; IMADW_DECL
 #define MIX_FI_(i) FFMA_(i) IMADW_(i)
 BENCH_KERNEL(k_mix_ffma_imadw, MIX_FI_DECL, REP8(MIX_FI_), F_SINK ^ (unsigned)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7))
+// packed FP32 against the integer multiplier: do FFMA2 and IMAD.WIDE share the FMA-heavy pipe?
+#define MIX_F2I_DECL FFMA2_DECL; unsigned long long w0 = u0x, w1 = w0 + 1, w2 = w0 + 2, w3 = w0 + 3; const unsigned ka = seed | 0xD2511F53u
+#define IMADW4_(i) asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(w##i) : "r"(ka));
+#define MIX_F2I_(i) FFMA2_(i) IMADW4_(i)
+__global__ void __launch_bounds__(kBlock) k_mix_ffma2_imadw(Out* out, unsigned seed)
+{
+    const unsigned u0x = seed + threadIdx.x;
+    MIX_F2I_DECL;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters; ++it) { REP4(MIX_F2I_) REP4(MIX_F2I_) }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x].cycles = t1 - t0;
+    if ((unsigned)(p0 ^ p1 ^ p2 ^ p3 ^ w0 ^ w1 ^ w2 ^ w3) == 0x12345u) out[blockIdx.x].sink = 1;
+}
+// scalar FMUL against the integer multiplier (FMUL may use the FMA-lite pipe)
+#define MIX_MI_(i) FMUL_(i) IMADW_(i)
+BENCH_KERNEL(k_mix_fmul_imadw, MIX_FI_DECL, REP8(MIX_MI_), F_SINK ^ (unsigned)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7))
+// 2 scalar FFMA per IMAD.WIDE
+#define MIX_2FI_(i) FFMA_(i) FFMA_(i) IMADW_(i)
+BENCH_KERNEL(k_mix_2ffma_imadw, MIX_FI_DECL, REP8(MIX_2FI_), F_SINK ^ (unsigned)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7))
+// FFMA2 + LOP3
+#define MIX_F2L_DECL FFMA2_DECL; U_DECL
+#define MIX_F2L_(i) FFMA2_(i) LOP3_(i)
+BENCH_KERNEL(k_mix_ffma2_lop3, MIX_F2L_DECL, REP4(MIX_F2L_) REP4(MIX_F2L_), (unsigned)(p0 ^ p1 ^ p2 ^ p3) ^ U_SINK)
 // 7 FFMA : 1 MUFU
 #define MIX_FM_(i) FFMA_(i) FFMA_(i)
 BENCH_KERNEL(k_mix_14ffma_2mufu, F_DECL, REP8(MIX_FM_) LG2_(0) SQRT_(1), F_SINK)
@@ -294,6 +321,10 @@ int main(int argc, char** argv)
     SIMPLE(k_mix_ffma_lop3, 16);
     SIMPLE(k_mix_imadw_lop3, 16);
     SIMPLE(k_mix_ffma_imadw, 16);
+    SIMPLE(k_mix_ffma2_imadw, 16);
+    SIMPLE(k_mix_fmul_imadw, 16);
+    SIMPLE(k_mix_2ffma_imadw, 24);
+    SIMPLE(k_mix_ffma2_lop3, 16);
     SIMPLE(k_mix_14ffma_2mufu, 18);
     SIMPLE(k_mix_8ffma_8lop3_2mufu, 18);
     SIMPLE(k_philox10, 80);     // 2 x (20 IMAD.WIDE + 20 LOP3), key schedule folded by ptxas

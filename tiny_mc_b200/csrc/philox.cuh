@@ -34,6 +34,25 @@ inline void philox_expand_key(uint64_t seed, PhiloxKeys* out)
 }
 
 #ifdef __CUDACC__
+// rounds FIRST .. LAST-1 of Philox4x32 on the state (c0, c1, c2, c3)
+template <int FIRST, int LAST>
+__device__ __forceinline__ void philox4x32_rounds(const PhiloxKeys& keys, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                  uint32_t c3, uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = FIRST; r < LAST; ++r) {
+        const uint64_t p0 = static_cast<uint64_t>(kPhiloxM0) * c0;  // IMAD.WIDE.U32
+        const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;
+        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ keys.k[2 * r];      // LOP3
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ keys.k[2 * r + 1];  // LOP3
+        c1 = static_cast<uint32_t>(p1);
+        c3 = static_cast<uint32_t>(p0);
+        c0 = n0;
+        c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 template <int ROUNDS>
 __device__ __forceinline__ void philox4x32(const PhiloxKeys& keys, uint32_t c0, uint32_t c1, uint32_t c2,
                                            uint32_t c3, uint32_t (&out)[4])

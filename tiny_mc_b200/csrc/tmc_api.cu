@@ -60,6 +60,7 @@ struct Options {
     int blocks_per_sm = 0;   // 0 = occupancy
     int flush_iters = 0;     // 0 = auto
     int nccl_reduce = 1;
+    int tally_layout = 0;    // 0 = auto, 1 = plain per-block histogram, 2 = lane-private
 };
 
 struct Lib {
@@ -135,27 +136,53 @@ int make_plan(const tmc_params* p, Plan* pl)
 
 using KernelFn = void (*)(const WalkArgs);
 
-template <int ROUNDS>
+// Block shapes: threads per block (two photons per thread) x the residency the register
+// budget is compiled for.  Lane-private tallies cost 32 KB + SHELLS * 256 B of shared memory
+// per block, so small grids run several 128/256-thread blocks per SM; the plain layout
+// (SHELLS > 760) runs one 512-thread block per SM.
+template <int ROUNDS, bool LANE_PRIVATE>
 KernelFn kernel_for_block(int block)
 {
     switch (block) {
-    case 128: return tmc::photon_walk_kernel<ROUNDS, 128, 8>;
-    case 256: return tmc::photon_walk_kernel<ROUNDS, 256, 4>;
-    case 512: return tmc::photon_walk_kernel<ROUNDS, 512, 2>;
-    case 1024: return tmc::photon_walk_kernel<ROUNDS, 1024, 1>;
+    case 128: return tmc::photon_walk_kernel<ROUNDS, 128, 4, LANE_PRIVATE>;
+    case 256: return tmc::photon_walk_kernel<ROUNDS, 256, 2, LANE_PRIVATE>;
+    case 512: return tmc::photon_walk_kernel<ROUNDS, 512, 1, LANE_PRIVATE>;
+    case 1024: return tmc::photon_walk_kernel<ROUNDS, 1024, 1, LANE_PRIVATE>;
     default: return nullptr;
     }
 }
 
-KernelFn pick_kernel(int rounds, int block)
+KernelFn pick_kernel(int rounds, int block, bool lane_private)
 {
     switch (rounds) {
-    case 7: return kernel_for_block<7>(block);
-    case 8: return kernel_for_block<8>(block);
-    case 9: return kernel_for_block<9>(block);
-    case 10: return kernel_for_block<10>(block);
+    case 7: return lane_private ? kernel_for_block<7, true>(block) : kernel_for_block<7, false>(block);
+    case 8: return lane_private ? kernel_for_block<8, true>(block) : kernel_for_block<8, false>(block);
+    case 9: return lane_private ? kernel_for_block<9, true>(block) : kernel_for_block<9, false>(block);
+    case 10: return lane_private ? kernel_for_block<10, true>(block) : kernel_for_block<10, false>(block);
     default: return nullptr;
     }
+}
+
+// (cos, sin)(2 pi i / 4096) in float, computed in double on the host and uploaded once per
+// device; every block stages it into shared memory (walk_kernel.cuh: spin()).
+const float2* g_azimuth[64] = {};
+
+int azimuth_table(int device, const float2** out)
+{
+    if (device < 0 || device >= 64) return fail(TMC_ERR_BAD_ARG, "device %d out of range", device);
+    if (!g_azimuth[device]) {
+        std::vector<float2> h(tmc::kAzimuthEntries);
+        for (int i = 0; i < tmc::kAzimuthEntries; ++i) {
+            const double phi = 6.283185307179586476925 * static_cast<double>(i) / tmc::kAzimuthEntries;
+            h[i] = make_float2(static_cast<float>(std::cos(phi)), static_cast<float>(std::sin(phi)));
+        }
+        float2* d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(float2)));
+        CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        g_azimuth[device] = d;
+    }
+    *out = g_azimuth[device];
+    return TMC_OK;
 }
 
 struct LaunchCfg {
@@ -166,35 +193,88 @@ struct LaunchCfg {
     uint32_t flush_iters;
 };
 
+// Per-device and per-kernel facts are looked up once: cudaGetDeviceProperties and
+// cudaFuncSetAttribute cost milliseconds, and the device-resident entry point is called per step.
+struct DeviceFacts {
+    bool known = false;
+    int rc = TMC_OK;
+    int sms = 0;
+};
+DeviceFacts g_facts[64];
+
+struct KernelFacts {
+    KernelFn fn;
+    int device;
+    int block;
+    size_t smem;
+    int per_sm;
+};
+std::vector<KernelFacts> g_kernel_facts;
+
+int check_device_arch(int dev);
+
+int device_facts(int dev, int* sms)
+{
+    if (dev < 0 || dev >= 64) return fail(TMC_ERR_NO_DEVICE, "CUDA device %d out of range", dev);
+    DeviceFacts& f = g_facts[dev];
+    if (!f.known) {
+        f.rc = check_device_arch(dev);
+        if (f.rc == TMC_OK) CUDA_TRY(cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, dev));
+        f.known = (f.rc == TMC_OK);
+        if (f.rc) return f.rc;
+    }
+    *sms = f.sms;
+    return TMC_OK;
+}
+
+int kernel_occupancy(KernelFn fn, int block, size_t smem, int* per_sm)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    for (const KernelFacts& k : g_kernel_facts)
+        if (k.fn == fn && k.device == dev && k.block == block && k.smem == smem) {
+            *per_sm = k.per_sm;
+            return TMC_OK;
+        }
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, block, smem));
+    g_kernel_facts.push_back(KernelFacts{ fn, dev, block, smem, *per_sm });
+    return TMC_OK;
+}
+
 int configure_launch(const tmc_params* p, int device_sms, uint64_t count, uint32_t flush_override, LaunchCfg* cfg)
 {
-    const size_t smem = static_cast<size_t>(2) * p->shells * sizeof(uint32_t);
+    bool lane_private = p->shells <= tmc::kLanePrivateMaxShells;
+    if (g.opt.tally_layout == 1) lane_private = false;
+    if (g.opt.tally_layout == 2 && !lane_private)
+        return fail(TMC_ERR_BAD_ARG, "SHELLS=%u is too large for lane-private tallies (max %u)", p->shells, tmc::kLanePrivateMaxShells);
+    const size_t smem = tmc::walk_smem_bytes(p->shells, lane_private);
     if (smem > 227u * 1024u)
         return fail(TMC_ERR_BAD_ARG, "SHELLS=%u needs %zu B of shared memory per block (> 227 KB)", p->shells, smem);
     int block = g.opt.block_threads;
-    if (block == 0) block = (smem > 56u * 1024u) ? 1024 : 256;
-    KernelFn fn = pick_kernel(g.opt.philox_rounds, block);
+    if (block == 0) block = lane_private ? 256 : 512;
+    KernelFn fn = pick_kernel(g.opt.philox_rounds, block, lane_private);
     if (!fn) return fail(TMC_ERR_BAD_ARG, "no kernel for philox_rounds=%d block_threads=%d", g.opt.philox_rounds, block);
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
+    int orc = kernel_occupancy(fn, block, smem, &per_sm);
+    if (orc) return orc;
     if (per_sm < 1) return fail(TMC_ERR_CUDA, "kernel does not fit on an SM (block=%d smem=%zu)", block, smem);
     if (g.opt.blocks_per_sm > 0 && g.opt.blocks_per_sm < per_sm) per_sm = g.opt.blocks_per_sm;
     uint64_t grid = static_cast<uint64_t>(device_sms) * per_sm;
-    const uint64_t needed = (count + block - 1) / block;
+    const uint64_t needed = (count + 2 * block - 1) / (2 * block);   // two photons per thread
     if (needed < grid) grid = needed ? needed : 1;
     uint32_t flush = flush_override ? flush_override : static_cast<uint32_t>(g.opt.flush_iters);
     if (flush == 0) {
-        // Hottest regular bin receives <~1.5 % of a block's events; with 2^21-scale deposits a
-        // 32-iteration interval leaves > 10x head-room below the 2^31 check.
-        // Wide grids spread the events over more bins, so the interval can grow with SHELLS.
-        flush = 32u;
-        if (p->shells > 512u) flush = 32u * (p->shells / 512u);
-        if (flush > 512u) flush = 512u;
-        flush = flush * 256u / static_cast<uint32_t>(block);
-        if (flush < 8u) flush = 8u;
+        // One iteration = 4 events per thread, deposits < 2^21.  Lane-private: the hottest
+        // (shell, lane) slot is the overflow bin's, <= 67 % / 32 of a block's events at a mean
+        // deposit of ~0.15 * 2^21 => 256 iterations of 256 threads stay > 5x below the 2^31
+        // check.  Plain layout: the hottest bin takes ~0.1 % of the events of a fine grid, ~1.5 %
+        // of a coarse one.  A tripped check is retried with a shorter interval.
+        if (lane_private) flush = 256u * 256u / static_cast<uint32_t>(block);
+        else flush = (p->shells >= 4096u ? 128u : 16u) * 512u / static_cast<uint32_t>(block);
+        if (flush < 4u) flush = 4u;
     }
-    if (flush > 1000u) flush = 1000u;   // per-thread overflow-bin registers: 2*flush*2^21 < 2^32
+    if (flush > 4096u) flush = 4096u;
     cfg->fn = fn;
     cfg->block = block;
     cfg->grid = static_cast<int>(grid);
@@ -203,13 +283,18 @@ int configure_launch(const tmc_params* p, int device_sms, uint64_t count, uint32
     return TMC_OK;
 }
 
+// Enqueue the walk over [first, first + count) on `stream` of the current device.  The kernel
+// addresses photons with 32-bit offsets inside one 2^32 window of the global index space, so
+// the range is cut at multiples of 2^32 and into pieces of at most 2^30 photons.
 int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t first, uint64_t count,
-                 const LaunchCfg& cfg, unsigned long long* d_buf, cudaStream_t stream)
+                 int device_sms, uint32_t flush_override, unsigned long long* d_buf, cudaStream_t stream, LaunchCfg* first_cfg)
 {
     WalkArgs a;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int rc = azimuth_table(dev, &a.azimuth);
+    if (rc) return rc;
     tmc::philox_expand_key(seed, &a.keys);
-    a.first = first;
-    a.count = count;
     a.tallies = d_buf;
     a.counters = d_buf + 2ull * p->shells;
     a.shells_per_mfp = pl.shells_per_mfp;
@@ -220,9 +305,25 @@ int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t fi
     a.heat2_rshift = pl.sc.heat2_rshift;
     a.heat2_half = pl.heat2_half;
     a.roulette_thr = pl.sc.roulette_thr;
-    a.flush_iters = cfg.flush_iters;
-    void* params[] = { &a };
-    CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(cfg.fn), dim3(cfg.grid), dim3(cfg.block), params, cfg.smem, stream));
+    bool have_first = false;
+    while (count > 0) {
+        const uint64_t window_left = (1ull << 32) - (first & 0xFFFFFFFFull);
+        uint64_t n = count < (1ull << 30) ? count : (1ull << 30);
+        if (n > window_left) n = window_left;
+        LaunchCfg cfg{};
+        rc = configure_launch(p, device_sms, n, flush_override, &cfg);
+        if (rc) return rc;
+        if (!have_first && first_cfg) *first_cfg = cfg;
+        have_first = true;
+        a.first = first;
+        a.count = n;
+        a.flush_iters = cfg.flush_iters;
+        void* params[] = { &a };
+        CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(cfg.fn), dim3(cfg.grid), dim3(cfg.block), params, cfg.smem, stream));
+        g.info.gpu_launches += 1;
+        first += n;
+        count -= n;
+    }
     return TMC_OK;
 }
 
@@ -292,16 +393,11 @@ int run_range(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t first
         const uint64_t lo = first + count / ng * i + (static_cast<uint64_t>(i) < count % ng ? i : count % ng);
         const uint64_t n = count / ng + (static_cast<uint64_t>(i) < count % ng ? 1 : 0);
         CUDA_TRY(cudaSetDevice(d.id));
-        LaunchCfg cfg{};
-        rc = configure_launch(p, d.sms, n, flush_override, &cfg);
-        if (rc) return rc;
-        if (i == 0) cfg0 = cfg;
         CUDA_TRY(cudaMemsetAsync(d.d_buf, 0, words * sizeof(unsigned long long), d.stream));
         CUDA_TRY(cudaEventRecord(d.ev0, d.stream));
         if (n > 0) {
-            rc = enqueue_walk(p, pl, seed, lo, n, cfg, d.d_buf, d.stream);
+            rc = enqueue_walk(p, pl, seed, lo, n, d.sms, flush_override, d.d_buf, d.stream, i == 0 ? &cfg0 : nullptr);
             if (rc) return rc;
-            g.info.gpu_launches += 1;
         }
         CUDA_TRY(cudaEventRecord(d.ev1, d.stream));
     }
@@ -400,7 +496,7 @@ void accumulate_float(const tmc_params* p, const Plan& pl, const uint64_t* heat_
 extern "C" {
 
 int tmc_abi_version(void) { return TMC_ABI_VERSION; }
-const char* tmc_version(void) { return "tiny_mc_b200 0.1 (sm_100a, stream tmc-stream-1)"; }
+const char* tmc_version(void) { return "tiny_mc_b200 0.2 (sm_100a, stream tmc-stream-2)"; }
 const char* tmc_last_error(void) { return g.err.c_str(); }
 int tmc_device_count(void) { return g.inited ? static_cast<int>(g.devs.size()) : 0; }
 
@@ -473,10 +569,13 @@ int tmc_set_option(const char* name, long long value)
         if (value < 0 || value > 32) return fail(TMC_ERR_BAD_ARG, "blocks_per_sm must be 0..32");
         g.opt.blocks_per_sm = static_cast<int>(value);
     } else if (n == "flush_iters") {
-        if (value < 0 || value > 1000) return fail(TMC_ERR_BAD_ARG, "flush_iters must be 0..1000");
+        if (value < 0 || value > 4096) return fail(TMC_ERR_BAD_ARG, "flush_iters must be 0..4096");
         g.opt.flush_iters = static_cast<int>(value);
     } else if (n == "nccl_reduce") {
         g.opt.nccl_reduce = value ? 1 : 0;
+    } else if (n == "tally_layout") {
+        if (value < 0 || value > 2) return fail(TMC_ERR_BAD_ARG, "tally_layout must be 0 (auto), 1 (plain) or 2 (lane-private)");
+        g.opt.tally_layout = static_cast<int>(value);
     } else {
         return fail(TMC_ERR_BAD_ARG, "unknown option '%s'", name);
     }
@@ -529,25 +628,21 @@ int tmc_photons_device(const tmc_params* p, uint64_t seed, uint64_t first_photon
     if (rc) return rc;
     if (n_photons > (1ull << (62 - pl.sc.heat_shift)))
         return fail(TMC_ERR_BAD_ARG, "n_photons too large for one device call with heat_shift=%u; split the range", pl.sc.heat_shift);
-    int visible = 0;
-    cudaError_t e = cudaGetDeviceCount(&visible);
-    if (e != cudaSuccess || device < 0 || device >= visible)
-        return fail(TMC_ERR_NO_DEVICE, "CUDA device %d not available (no CPU fallback)", device);
-    rc = check_device_arch(device);
+    int sms = 0;
+    rc = device_facts(device, &sms);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(device));
-    int sms = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     if (n_photons == 0) return TMC_OK;
     LaunchCfg cfg{};
-    rc = configure_launch(p, sms, n_photons, 0, &cfg);
-    if (rc) return rc;
+    g.info.gpu_launches = 0;
+    rc = enqueue_walk(p, pl, seed, first_photon, n_photons, sms, 0, static_cast<unsigned long long*>(d_tallies),
+                      static_cast<cudaStream_t>(cuda_stream), &cfg);
     g.info.blocks_per_gpu = static_cast<uint32_t>(cfg.grid);
     g.info.threads_per_block = static_cast<uint32_t>(cfg.block);
     g.info.flush_iters = cfg.flush_iters;
     g.info.smem_bytes = static_cast<uint32_t>(cfg.smem);
     g.info.philox_rounds = static_cast<uint32_t>(g.opt.philox_rounds);
-    return enqueue_walk(p, pl, seed, first_photon, n_photons, cfg, static_cast<unsigned long long*>(d_tallies), static_cast<cudaStream_t>(cuda_stream));
+    return rc;
 }
 
 int tmc_last_run_info(tmc_run_info* out)
