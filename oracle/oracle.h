@@ -53,7 +53,7 @@ void orc_seed(int kind, unsigned seed);
 uint64_t orc_run_batch(const orc_optics* o, orc_photon_fn fn, int rng_kind, unsigned seed, uint64_t n_photons,
                        uint32_t chunk, double* heat, double* heat2, float* heat_f, float* heat2_f);
 
-/* ---- stream_replay.c : CPU replay of the product's stream "tmc-stream-1" ---- */
+/* ---- stream_replay.c : CPU replay of the product's stream "tmc-stream-3" ---- */
 
 typedef struct orc_fx_scales {
     uint32_t weight_one;     /* fixed-point value of weight 1.0 (= 2^heat_shift)        */
@@ -67,6 +67,11 @@ void orc_philox4x32(uint32_t rounds, const uint32_t ctr[4], const uint32_t key[2
 
 /* Fixed-point plan shared with the product (restated from DESIGN.md §4, not imported). */
 void orc_fx_plan(const orc_optics* o, orc_fx_scales* s);
+
+/* Deterministic weight schedule: generation g (= roulettes survived) starts at event
+ * first_event[g] (1-based) with weight w_start[g] and lasts n_events[g] events. */
+uint32_t orc_generation_plan(const orc_optics* o, uint32_t max_gen, uint32_t* first_event, uint32_t* n_events,
+                             uint32_t* w_start);
 
 /* Replay photons [first, first+n) of stream `seed`; ADD into u64 heat_fx/heat2_fx[shells].
  * Returns number of scatter events. */

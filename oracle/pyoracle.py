@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         l.orc_fx_plan.argtypes = [C.POINTER(Optics), C.POINTER(FxScales)]
         l.orc_replay.restype = C.c_uint64
         l.orc_replay.argtypes = [C.POINTER(Optics), C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        l.orc_generation_plan.restype = C.c_uint32
+        l.orc_generation_plan.argtypes = [C.POINTER(Optics), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = l
     return _lib
 
@@ -151,6 +153,14 @@ def replay(cfg, seed: int, first: int, n: int, rounds: int = 10):
     heat2 = np.zeros(o.shells, np.uint64)
     ev = lib().orc_replay(C.byref(o), rounds, seed, first, n, heat.ctypes.data, heat2.ctypes.data)
     return heat, heat2, int(ev)
+
+
+def generation_plan(cfg, max_gen: int = 8):
+    """(first_event, n_events, w_start) per generation of the deterministic weight schedule."""
+    o = optics(cfg)
+    a, b, c = (np.zeros(max_gen, np.uint32) for _ in range(3))
+    lib().orc_generation_plan(C.byref(o), max_gen, a.ctypes.data, b.ctypes.data, c.ctypes.data)
+    return a, b, c
 
 
 def fx_to_float64(cfg, heat_fx, heat2_fx):

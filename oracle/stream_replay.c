@@ -1,13 +1,19 @@
 /* oracle/stream_replay.c — TEST INFRASTRUCTURE ONLY (see oracle/README.md).
  *
  * CPU replay of the PRODUCT's random stream and fixed-point tally arithmetic
- * ("tmc-stream-2"), restated independently in scalar C with libm
+ * ("tmc-stream-3"), restated independently in scalar C with libm
  * (log2f / sqrtf, cos / sin in double for the azimuth table) standing in for the GPU's MUFU
  * approximations.
  *
- * Stream layout: photon i draws Philox4x32-R(counter = (i_lo, i_hi, block, 0), key = seed).
- *   block 0 : word 0 = roulette fate word, word 1 = launch direction, words 2-3 = first event;
- *   block b : words 0-1 = one event (step word, direction word), words 2-3 = the next event.
+ * Stream layout: photon i draws Philox4x32-R(counter = (i_lo, i_hi, block, 0), key = seed);
+ * one block = four words = THREE scatter events of 42 bits each.  Event e >= 1 of a photon is
+ * slot e % 3 of block e / 3 and uses word[slot] plus bits [10*slot, 10*slot+10) of word[3];
+ * pseudo-event 0 (block 0, slot 0) is the photon's roulette fate word.  Inside an event word v:
+ *   bits 10..31  step:      xi = 2 * (1.5 - f), f = 1 + (v >> 10) * 2^-23      (22 bits)
+ *   bits  1..9   cos theta: (2k + 1) / 512 - 1                                 ( 9 bits, midpoints)
+ *   word[3] slice: azimuth index into a 1024-entry (cos, sin) table            (10 bits)
+ * The direction is drawn at the START of an event (spin, then hop), so no direction is carried
+ * from one event to the next; the first event's direction is the isotropic launch direction.
  *
  * What it pins (tests/test_gpu_parity.py):
  *   - integer-exact: scatter events per photon, roulette fates, every deposit value and
@@ -80,20 +86,30 @@ void orc_fx_plan(const orc_optics* o, orc_fx_scales* s)
 
 typedef union { uint32_t u; float f; } bits32;
 
-/* New isotropic direction from one word (replaces the rejection loop of photon.c:35-43):
- * cos(theta) uniform from bits 9..31, azimuth index from bits 3..14 into a 4096-entry table of
- * (float)cos, (float)sin of 2 pi i / 4096 evaluated in double. */
-static void spin_direction(uint32_t wd, float* dx, float* dy, float* dz)
+#define AZIMUTH_ENTRIES 1024u
+
+/* Deterministic weight schedule: every photon of generation g (= number of
+ * roulettes survived) starts it with the same weight and needs the same number of events
+ * to fall below the roulette threshold.  Restated here independently of the product. */
+uint32_t orc_generation_plan(const orc_optics* o, uint32_t max_gen, uint32_t* first_event, uint32_t* n_events,
+                             uint32_t* w_start)
 {
-    bits32 cb;
-    cb.u = (wd >> 9) | 0x3F800000u;                   /* 1 + m * 2^-23 in [1, 2) */
-    const float ct = fmaf(cb.f, 2.0f, -3.0f);         /* exact */
-    const float nct = fmaf(cb.f, -2.0f, 3.0f);        /* exact */
-    const float st = sqrtf(fmaf(ct, nct, 1.0f));
-    const double phi = 6.283185307179586476925 * (double)((wd >> 3) & 4095u) / 4096.0;
-    *dx = ct;
-    *dy = st * (float)cos(phi);
-    *dz = st * (float)sin(phi);
+    orc_fx_scales s;
+    orc_fx_plan(o, &s);
+    uint32_t w = s.weight_one, e = 1, g = 0;
+    for (; g < max_gen; ++g) {
+        uint32_t k = 0;
+        first_event[g] = e;
+        w_start[g] = w;
+        do {
+            w -= (uint32_t)(((uint64_t)w * s.absorb_q32 + 0x80000000ull) >> 32);
+            ++k;
+        } while (w >= s.roulette_thr && k < 0x40000000u);
+        n_events[g] = k;
+        e += k;
+        w *= 10u;
+    }
+    return g;
 }
 
 uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n,
@@ -105,57 +121,68 @@ uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_
     const uint32_t last = o->shells - 1u;
     const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
     const uint64_t half = s.heat2_rshift ? ((uint64_t)1 << (s.heat2_rshift - 1)) : 0;
-    const float LN2 = 0.693147182464599609375f;          /* float(ln 2)      */
-    const float STEP_BIAS = 22.1807098388671875f;        /* float(32 * ln 2) */
+    const float LN2 = 0.693147182464599609375f;          /* float(ln 2)       */
     const uint32_t FATE_SURVIVE = 429496729u;            /* floor(0.1 * 2^32) */
+    static float az_cos[AZIMUTH_ENTRIES], az_sin[AZIMUTH_ENTRIES];
+    static int az_ready = 0;
+    if (!az_ready) {
+        for (uint32_t i = 0; i < AZIMUTH_ENTRIES; ++i) {
+            const double phi = 6.283185307179586476925 * (double)i / (double)AZIMUTH_ENTRIES;
+            az_cos[i] = (float)cos(phi);
+            az_sin[i] = (float)sin(phi);
+        }
+        az_ready = 1;
+    }
     uint64_t events = 0;
 
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t p = first + i;
-        float x = 0.0f, y = 0.0f, z = 0.0f;
-        float dx = 0.0f, dy = 0.0f, dz = 0.0f;
-        uint32_t w = s.weight_one;
-        uint32_t fate = 0;
-        int alive = 1;
-        for (uint32_t blk = 0; alive; ++blk) {
-            const uint32_t ctr[4] = { (uint32_t)p, (uint32_t)(p >> 32), blk, 0u };
-            uint32_t r[4];
-            orc_philox4x32(rounds, ctr, key, r);
-            int slot = 0;
-            if (blk == 0) { /* birth block: word 0 = roulette fate, word 1 = isotropic launch direction */
-                fate = r[0];
-                spin_direction(r[1], &dx, &dy, &dz);
-                slot = 1;
+        float x = 0.0f, y = 0.0f, z = 0.0f;   /* photon.c:12-14 */
+        uint32_t w = s.weight_one;            /* photon.c:18    */
+        uint32_t r[4] = { 0, 0, 0, 0 };
+        uint32_t have_blk = 0xFFFFFFFFu, fate = 0;
+        for (uint32_t e = 0;; ++e) {
+            /* pseudo-event 0 is the fate word; event e >= 1 is slot e % 3 of block e / 3 */
+            const uint32_t blk = e / 3u, slot = e % 3u;
+            if (blk != have_blk) {
+                const uint32_t ctr[4] = { (uint32_t)p, (uint32_t)(p >> 32), blk, 0u };
+                orc_philox4x32(rounds, ctr, key, r);
+                have_blk = blk;
             }
-            for (; slot < 2 && alive; ++slot) {
-                const uint32_t ws = r[2 * slot], wd = r[2 * slot + 1];
-                ++events;
-                /* hop: xi = (ws + 0.5) / 2^32 in float; t = -ln(xi) */
-                const float fxi = (float)ws + 0.5f;
-                const float t = fmaf(log2f(fxi), -LN2, STEP_BIAS);
-                x = fmaf(t, dx, x);
-                y = fmaf(t, dy, y);
-                z = fmaf(t, dz, z);
-                /* drop */
-                const float r2 = fmaf(z, z, fmaf(y, y, x * x));
-                const float rad = sqrtf(r2);
-                double sf = floor((double)rad * (double)spm);
-                uint32_t shell = (sf >= (double)last) ? last : (uint32_t)sf;
-                /* deposit = round(w * (1-albedo)): one 32x32+64 multiply-add, high word */
-                const uint32_t dep = (uint32_t)(((uint64_t)w * s.absorb_q32 + 0x80000000ull) >> 32);
-                w -= dep;
-                heat_fx[shell] += dep;
-                heat2_fx[shell] += ((uint64_t)dep * dep + half) >> s.heat2_rshift;
-                /* roulette */
-                if (w < s.roulette_thr) {
-                    if (fate < FATE_SURVIVE) {
-                        fate *= 10u;
-                        w *= 10u;
-                    } else {
-                        alive = 0;
-                    }
-                }
-                spin_direction(wd, &dx, &dy, &dz);
+            if (e == 0) {
+                fate = r[0];
+                continue;
+            }
+            const uint32_t v = r[slot], az = (r[3] >> (10u * slot)) & 1023u;
+            ++events;
+            /* spin (photon.c:35-43, sampled directly, BEFORE the hop so that no direction is
+             * carried between events): cos(theta) = (2k+1)/512 - 1 from bits 1..9, azimuth
+             * from a 1024-entry table indexed by 10 bits of word 3 */
+            const float ct = fmaf((float)(8388608u + ((v & 0x3FEu) | 1u)), 0.001953125f, -16385.0f);
+            const float st = sqrtf(fmaf(-ct, ct, 1.0f));
+
+            /* hop (photon.c:21-24): xi = 2 * (1.5 - f), f = 1 + (v >> 10) * 2^-23 */
+            bits32 fb;
+            fb.u = 0x3F800000u | (v >> 10);
+            const float t = fmaf(log2f(1.5f - fb.f), -LN2, -LN2);
+            const float ts = t * st;
+            x = fmaf(t, ct, x);
+            y = fmaf(ts, az_cos[az], y);
+            z = fmaf(ts, az_sin[az], z);
+            /* drop (photon.c:26-32) */
+            const float rad = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+            const double sf = floor((double)rad * (double)spm);
+            const uint32_t shell = (sf >= (double)last) ? last : (uint32_t)sf;
+            const uint32_t dep = (uint32_t)(((uint64_t)w * s.absorb_q32 + 0x80000000ull) >> 32);
+            w -= dep;
+            heat_fx[shell] += dep;
+            heat2_fx[shell] += ((uint64_t)dep * dep + half) >> s.heat2_rshift;
+            /* roulette (photon.c:45-49) */
+            if (w < s.roulette_thr) {
+                if (fate >= FATE_SURVIVE)
+                    break;
+                fate *= 10u;
+                w *= 10u;
             }
         }
     }

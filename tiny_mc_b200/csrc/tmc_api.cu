@@ -32,6 +32,8 @@ struct Plan {
     tmc_scales sc;
     uint32_t weight_one;
     uint32_t heat2_half;
+    uint32_t n_gen;
+    tmc::GenPlan gen[tmc::kMaxGenerations];   // the deterministic weight schedule, per generation
 };
 
 struct Device {
@@ -131,21 +133,77 @@ int make_plan(const tmc_params* p, Plan* pl)
     pl->sc.heat2_rshift = (2 * bits > 22) ? 2 * bits - 22 : 0;
     pl->heat2_half = pl->sc.heat2_rshift ? (1u << (pl->sc.heat2_rshift - 1)) : 0u;
     pl->sc.roulette_thr = static_cast<uint32_t>(std::floor(0.001 * pl->weight_one + 0.5));
+    // Generation g = number of roulettes survived.  Every photon of a generation starts it with
+    // the same weight and needs the same number of events to fall below the threshold
+    // (reference photon.c:32,45-48: w *= albedo per event, x10 per survived roulette).
+    uint32_t w = pl->weight_one, e = 1;
+    pl->n_gen = tmc::kMaxGenerations;
+    for (uint32_t g = 0; g < pl->n_gen; ++g) {
+        uint32_t k = 0;
+        pl->gen[g].first_event = e;
+        pl->gen[g].w_start = w;
+        do {
+            w -= static_cast<uint32_t>((static_cast<uint64_t>(w) * pl->sc.absorb_q32 + 0x80000000ull) >> 32);
+            ++k;
+        } while (w >= pl->sc.roulette_thr && k < (1u << 28));
+        if (w >= pl->sc.roulette_thr)
+            return fail(TMC_ERR_BAD_ARG, "MU_A / (MU_A + MU_S) = %g is too small: a photon needs > 2^28 events per generation", absorb);
+        pl->gen[g].n_events = k;
+        e += k;
+        w *= 10u;
+    }
+    return TMC_OK;
+}
+
+// (deposit, rescaled deposit^2) of every event number of the deterministic weight schedule
+// (Plan::gen), computed with the exact integer recurrence and uploaded once per device and
+// optics.  Tables are never overwritten (kernels on other streams may still read them).
+struct DepositTable {
+    int device;
+    uint32_t absorb_q32, weight_one, heat2_rshift, roulette_thr;
+    uint2* d_table;
+};
+std::vector<DepositTable> g_deposit_tables;
+
+int deposit_table(int device, const Plan& pl, const uint2** out)
+{
+    for (const DepositTable& t : g_deposit_tables)
+        if (t.device == device && t.absorb_q32 == pl.sc.absorb_q32 && t.weight_one == pl.weight_one &&
+            t.heat2_rshift == pl.sc.heat2_rshift && t.roulette_thr == pl.sc.roulette_thr) {
+            *out = t.d_table;
+            return TMC_OK;
+        }
+    const tmc::GenPlan& last = pl.gen[pl.n_gen - 1];
+    std::vector<uint2> h(static_cast<size_t>(last.first_event) + last.n_events, make_uint2(0u, 0u));
+    for (uint32_t g = 0; g < pl.n_gen; ++g) {
+        uint32_t w = pl.gen[g].w_start;
+        for (uint32_t k = 0; k < pl.gen[g].n_events; ++k) {
+            const uint32_t dep = static_cast<uint32_t>((static_cast<uint64_t>(w) * pl.sc.absorb_q32 + 0x80000000ull) >> 32);
+            const uint32_t dep2 = static_cast<uint32_t>((static_cast<uint64_t>(dep) * dep + pl.heat2_half) >> pl.sc.heat2_rshift);
+            h[pl.gen[g].first_event + k] = make_uint2(dep, dep2);
+            w -= dep;
+        }
+    }
+    uint2* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(uint2)));
+    CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    g_deposit_tables.push_back(DepositTable{ device, pl.sc.absorb_q32, pl.weight_one, pl.sc.heat2_rshift, pl.sc.roulette_thr, d });
+    *out = d;
     return TMC_OK;
 }
 
 using KernelFn = void (*)(const WalkArgs);
 
 // Block shapes: threads per block (two photons per thread) x the residency the register
-// budget is compiled for.  Lane-private tallies cost 32 KB + SHELLS * 256 B of shared memory
-// per block, so small grids run several 128/256-thread blocks per SM; the plain layout
-// (SHELLS > 760) runs one 512-thread block per SM.
+// budget is compiled for.  A block needs 8 KB (azimuth table) + its tallies (SHELLS * 256 B
+// lane-private, else (SHELLS + 31) * 8 B) + 5 KB of survivor queues per warp: small grids run
+// three 256-thread blocks per SM, the plain layout (SHELLS > 512) one 512-thread block.
 template <int ROUNDS, bool LANE_PRIVATE>
 KernelFn kernel_for_block(int block)
 {
     switch (block) {
     case 128: return tmc::photon_walk_kernel<ROUNDS, 128, 4, LANE_PRIVATE>;
-    case 256: return tmc::photon_walk_kernel<ROUNDS, 256, 2, LANE_PRIVATE>;
+    case 256: return tmc::photon_walk_kernel<ROUNDS, 256, 3, LANE_PRIVATE>;
     case 512: return tmc::photon_walk_kernel<ROUNDS, 512, 1, LANE_PRIVATE>;
     case 1024: return tmc::photon_walk_kernel<ROUNDS, 1024, 1, LANE_PRIVATE>;
     default: return nullptr;
@@ -163,7 +221,7 @@ KernelFn pick_kernel(int rounds, int block, bool lane_private)
     }
 }
 
-// (cos, sin)(2 pi i / 4096) in float, computed in double on the host and uploaded once per
+// (cos, sin)(2 pi i / 1024) in float, computed in double on the host and uploaded once per
 // device; every block stages it into shared memory (walk_kernel.cuh: spin()).
 const float2* g_azimuth[64] = {};
 
@@ -242,17 +300,22 @@ int kernel_occupancy(KernelFn fn, int block, size_t smem, int* per_sm)
     return TMC_OK;
 }
 
+double shells_per_mfp_of(const tmc_params* p)
+{
+    return 1e4 / static_cast<double>(p->microns_per_shell) / static_cast<double>(p->mu_a + p->mu_s);
+}
+
 int configure_launch(const tmc_params* p, int device_sms, uint64_t count, uint32_t flush_override, LaunchCfg* cfg)
 {
     bool lane_private = p->shells <= tmc::kLanePrivateMaxShells;
     if (g.opt.tally_layout == 1) lane_private = false;
     if (g.opt.tally_layout == 2 && !lane_private)
         return fail(TMC_ERR_BAD_ARG, "SHELLS=%u is too large for lane-private tallies (max %u)", p->shells, tmc::kLanePrivateMaxShells);
-    const size_t smem = tmc::walk_smem_bytes(p->shells, lane_private);
-    if (smem > 227u * 1024u)
-        return fail(TMC_ERR_BAD_ARG, "SHELLS=%u needs %zu B of shared memory per block (> 227 KB)", p->shells, smem);
     int block = g.opt.block_threads;
     if (block == 0) block = lane_private ? 256 : 512;
+    const size_t smem = tmc::walk_smem_bytes(p->shells, lane_private, static_cast<uint32_t>(block));
+    if (smem > 227u * 1024u)
+        return fail(TMC_ERR_BAD_ARG, "SHELLS=%u with %d-thread blocks needs %zu B of shared memory per block (> 227 KB)", p->shells, block, smem);
     KernelFn fn = pick_kernel(g.opt.philox_rounds, block, lane_private);
     if (!fn) return fail(TMC_ERR_BAD_ARG, "no kernel for philox_rounds=%d block_threads=%d", g.opt.philox_rounds, block);
     int per_sm = 0;
@@ -261,18 +324,27 @@ int configure_launch(const tmc_params* p, int device_sms, uint64_t count, uint32
     if (per_sm < 1) return fail(TMC_ERR_CUDA, "kernel does not fit on an SM (block=%d smem=%zu)", block, smem);
     if (g.opt.blocks_per_sm > 0 && g.opt.blocks_per_sm < per_sm) per_sm = g.opt.blocks_per_sm;
     uint64_t grid = static_cast<uint64_t>(device_sms) * per_sm;
-    const uint64_t needed = (count + 2 * block - 1) / (2 * block);   // two photons per thread
+    const uint64_t warps = static_cast<uint64_t>(block) / 32u;
+    const uint64_t needed = ((count + 63) / 64 + warps - 1) / warps;   // cohorts of 64 photons, one per warp
     if (needed < grid) grid = needed ? needed : 1;
     uint32_t flush = flush_override ? flush_override : static_cast<uint32_t>(g.opt.flush_iters);
     if (flush == 0) {
-        // One iteration = 4 events per thread, deposits < 2^21.  Lane-private: the hottest
-        // (shell, lane) slot is the overflow bin's, <= 67 % / 32 of a block's events at a mean
-        // deposit of ~0.15 * 2^21 => 256 iterations of 256 threads stay > 5x below the 2^31
-        // check.  Plain layout: the hottest bin takes ~0.1 % of the events of a fine grid, ~1.5 %
-        // of a coarse one.  A tripped check is retried with a shorter interval.
-        if (lane_private) flush = 256u * 256u / static_cast<uint32_t>(block);
-        else flush = (p->shells >= 4096u ? 128u : 16u) * 512u / static_cast<uint32_t>(block);
-        if (flush < 4u) flush = 4u;
+        // Philox blocks (3 events for each of a warp's 64 photons) between two drains of the u32
+        // block histograms; deposits are < 2^21.
+        if (lane_private) {
+            // A (shell, lane) slot only ever sees the 2 photons per warp of its own lane: even if
+            // all of them sat in one shell at full weight, 2^32 / (2 * warps * 3 * 2^21) blocks
+            // cannot wrap the word; the 2^31 check then catches anything above half of that.
+            flush = static_cast<uint32_t>(2048u / (6u * warps));
+        } else {
+            // One histogram per block: bound the busiest shell by the first-collision share
+            // 1 - exp(-1/shells_per_mfp) <= 1/shells_per_mfp of a block's photons (x2 margin).
+            double share = 2.0 / static_cast<double>(shells_per_mfp_of(p));
+            if (share > 1.0) share = 1.0;
+            const double blocks = 2147483648.0 / (64.0 * static_cast<double>(warps) * 3.0 * share * 2097152.0);
+            flush = blocks > 64.0 ? 64u : (blocks < 1.0 ? 1u : static_cast<uint32_t>(blocks));
+        }
+        if (flush < 1u) flush = 1u;
     }
     if (flush > 4096u) flush = 4096u;
     cfg->fn = fn;
@@ -300,11 +372,10 @@ int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t fi
     a.shells_per_mfp = pl.shells_per_mfp;
     a.shells = p->shells;
     a.last_bits = tmc::kMagicBits + p->shells - 1u;
-    a.weight_one = pl.weight_one;
-    a.absorb_q32 = pl.sc.absorb_q32;
-    a.heat2_rshift = pl.sc.heat2_rshift;
-    a.heat2_half = pl.heat2_half;
-    a.roulette_thr = pl.sc.roulette_thr;
+    rc = deposit_table(dev, pl, &a.deposits);
+    if (rc) return rc;
+    a.n_gen = pl.n_gen;
+    for (uint32_t i = 0; i < pl.n_gen; ++i) a.gen[i] = pl.gen[i];
     bool have_first = false;
     while (count > 0) {
         const uint64_t window_left = (1ull << 32) - (first & 0xFFFFFFFFull);
@@ -317,7 +388,7 @@ int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t fi
         have_first = true;
         a.first = first;
         a.count = n;
-        a.flush_iters = cfg.flush_iters;
+        a.flush_blocks = cfg.flush_iters;
         void* params[] = { &a };
         CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(cfg.fn), dim3(cfg.grid), dim3(cfg.block), params, cfg.smem, stream));
         g.info.gpu_launches += 1;
@@ -496,7 +567,7 @@ void accumulate_float(const tmc_params* p, const Plan& pl, const uint64_t* heat_
 extern "C" {
 
 int tmc_abi_version(void) { return TMC_ABI_VERSION; }
-const char* tmc_version(void) { return "tiny_mc_b200 0.2 (sm_100a, stream tmc-stream-2)"; }
+const char* tmc_version(void) { return "tiny_mc_b200 0.3 (sm_100a, stream tmc-stream-3)"; }
 const char* tmc_last_error(void) { return g.err.c_str(); }
 int tmc_device_count(void) { return g.inited ? static_cast<int>(g.devs.size()) : 0; }
 

@@ -1,29 +1,37 @@
-// walk_kernel.cuh — the photon random walk as a persistent-thread sm_100a kernel.
+// walk_kernel.cuh — the photon random walk as a persistent-warp sm_100a kernel.
 //
 // Replaces the reference hot path: photon() (reference photon.c:6-51) and the loop that
 // drives it (reference tiny_mc.c:47-49).  One launch simulates a whole range of photons.
 //
 // Design:
-//  * persistent threads, TWO photons per thread: each thread owns two static strided lists of
-//    photon indices and regenerates the next photon in place in the Philox block after the
-//    one in which the current photon is killed by roulette, so warps never wait for their
-//    longest-lived photon.  The two photons of a thread are processed as packed FP32 pairs
-//    (Blackwell FFMA2 / FMUL2 / FADD2: two FMAs per issue slot) and give every thread two
-//    independent dependency chains;
-//  * random stream "tmc-stream-2": Philox4x32-R keyed by the seed, counter = (photon index,
-//    block number).  One Philox call yields the four words of TWO scatter events; the birth
-//    block gives the photon's roulette fate word, its (isotropic) launch direction and its
-//    first event;
-//  * weights are 32-bit fixed point, deposits are exact integers, tallies are u32 shared-
-//    memory histograms privatised per block AND per lane ([shell][heat|heat2][lane]: every
-//    lane of a warp owns its own bank, so an ATOMS.ADD is always one conflict-free wavefront,
-//    also for the overflow bin that takes 20-67 % of the events), drained with atomicExch
-//    every `flush_iters` iterations into u64 global tallies => the result is independent of
-//    thread/block/GPU count and of atomic ordering (bit-reproducible).  Grids too fine for
-//    per-lane copies (SHELLS > 760) use one u32 histogram per block plus 32 per-lane slots for
-//    the overflow bin;
-//  * MUFU: lg2 (step), sqrt (radius), sqrt (sin theta) = 3 per event; the azimuth (cos, sin)
-//    comes from a 4096-entry table in shared memory (one LDS.64).
+//  * The weight of a photon is a pure function of how many events it has lived: every event
+//    removes the fraction (1-albedo) (photon.c:30-32) and the roulette (photon.c:45-49) is the
+//    only random influence, multiplying by exactly 10 when it is survived.  So all photons of
+//    one GENERATION (= number of roulettes survived) carry the same weight at the same event
+//    number, reach the roulette at the same event, and deposit the same amount per event.
+//  * Persistent warps therefore walk COHORTS of 64 photons of one generation (two per lane,
+//    two independent dependency chains per thread) in lock step: no lane ever waits for
+//    another, the weight / deposit arithmetic is warp-uniform (one computation per thread
+//    pair instead of per photon), and nothing in the event loop branches per lane.  When a
+//    generation ends, every lane plays roulette with its photon's fate word; the ~10 %
+//    survivors are parked in a per-warp shared-memory queue of the next generation, the warp
+//    immediately regenerates 64 fresh photons in place (or, when 64 survivors have
+//    accumulated, a full cohort of them).  Generations beyond the second (1e-3 of the
+//    photons) continue in place with the dead lanes masked.
+//  * Random stream "tmc-stream-3": Philox4x32-R keyed by the seed, counter = (photon index,
+//    block).  One Philox block = THREE events of 42 bits; event e of a photon is slot e % 3 of
+//    block e / 3, pseudo-event 0 is the roulette fate word.  A photon's trajectory depends on
+//    (seed, photon index) only.
+//  * Deposits are exact integers (32-bit fixed-point weights); tallies are u32 shared-memory
+//    histograms privatised per block AND per lane ([shell][heat|heat2][lane]: every lane of a
+//    warp owns its own bank, an ATOMS.ADD is always one conflict-free wavefront, also for the
+//    overflow bin that takes 20-67 % of the events), drained with atomicExch into u64 global
+//    tallies => the result does not depend on thread/block/GPU count or on atomic ordering.
+//    Grids too fine for per-lane copies use one u32 histogram per block plus 32 per-lane
+//    slots for the overflow bin.
+//  * Per event and photon: 3 MUFU (lg2 for the step, sqrt for sin(theta), sqrt for the
+//    radius), 12 FP32 operations, 2 shared atomics, one LDS.64 for the azimuth (cos, sin)
+//    table and a third of a Philox block.
 #pragma once
 #include <cstdint>
 
@@ -31,10 +39,19 @@
 
 namespace tmc {
 
-constexpr int kAzimuthBits = 12;
-constexpr int kAzimuthEntries = 1 << kAzimuthBits;          // (cos, sin) pairs, 32 KB
+constexpr int kAzimuthEntries = 1024;                       // (cos, sin)(2 pi i / 1024): 8 KB
 constexpr uint32_t kAzimuthBytes = kAzimuthEntries * 8u;
-constexpr uint32_t kLanePrivateMaxShells = 760u;            // 32 KB table + shells * 256 B <= 227 KB
+constexpr int kMaxGenerations = 24;                         // P(survive 24 roulettes) = 1e-24
+constexpr uint32_t kQueueCap = 128u;                        // entries per queued generation and warp
+constexpr uint32_t kQueueFields = 5u;                       // x, y, z, photon offset, fate word
+constexpr uint32_t kQueueBytesPerWarp = 2u * kQueueFields * kQueueCap * 4u;   // generations 1 and 2
+constexpr uint32_t kLanePrivateMaxShells = 512u;
+
+struct GenPlan {
+    uint32_t first_event;   // 1-based number of the generation's first event
+    uint32_t n_events;      // events until the weight falls below the roulette threshold
+    uint32_t w_start;       // fixed-point weight at the start of the generation
+};
 
 struct WalkArgs {
     PhiloxKeys keys;                // constant-bank round keys
@@ -42,27 +59,24 @@ struct WalkArgs {
     uint64_t count;                 // cross a multiple of 2^32, and count <= 2^30 (the host splits)
     unsigned long long* tallies;    // global u64[2*shells]: heat_fx | heat2_fx
     unsigned long long* counters;   // global u64[4]: events, photons, range flag, -
-    const float2* azimuth;          // global (cos, sin)(2 pi i / 4096), i < 4096
+    const float2* azimuth;          // global (cos, sin)(2 pi i / 1024)
+    const uint2* deposits;          // global (deposit, rescaled deposit^2) of event e, e = 1 .. last event of gen[n_gen-1]
     float shells_per_mfp;           // reference photon.c:9
     uint32_t shells;                // SHELLS (reference params.h:5)
     uint32_t last_bits;             // 0x4B000000 + SHELLS-1 : clamp in the magic-number domain
-    uint32_t weight_one;            // fixed-point 1.0
-    uint32_t absorb_q32;            // round((1-albedo) * 2^32)  (reference photon.c:8,30)
-    uint32_t heat2_rshift;          // deposit^2 >> heat2_rshift
-    uint32_t heat2_half;            // rounding constant for that shift
-    uint32_t roulette_thr;          // fixed-point 0.001 (reference photon.c:45)
-    uint32_t flush_iters;           // iterations between drains of the shared histograms
+    uint32_t flush_blocks;          // Philox blocks (3 events) a warp walks between drains
+    uint32_t n_gen;                 // generations in `gen` (a photon surviving them all is dropped)
+    GenPlan gen[kMaxGenerations];
 };
 
 constexpr uint32_t kMagicBits = 0x4B000000u;     // float 2^23
 constexpr uint32_t kFateSurvive = 429496729u;    // floor(0.1 * 2^32): survive roulette iff fate < this
 constexpr float kLn2 = 0.693147182464599609375f;
-constexpr float kStepBias = 22.1807098388671875f;  // 32 * ln 2
 
 // shared-memory bytes of one block
-inline uint32_t walk_smem_bytes(uint32_t shells, bool lane_private)
+inline uint32_t walk_smem_bytes(uint32_t shells, bool lane_private, uint32_t block_threads)
 {
-    return kAzimuthBytes + (lane_private ? shells * 256u : 2u * (shells + 31u) * 4u);
+    return kAzimuthBytes + (lane_private ? shells * 256u : 2u * (shells + 31u) * 4u) + (block_threads / 32u) * kQueueBytesPerWarp;
 }
 
 #ifdef __CUDACC__
@@ -79,35 +93,12 @@ __device__ __forceinline__ float mufu_sqrt(float v)
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
-// hi word of a*b + c (64-bit accumulate): one IMAD.WIDE.U32
+// a*b + c with a 64-bit accumulator: one IMAD.WIDE.U32
 __device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
 {
     uint64_t r;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
     return r;
-}
-// Loop-invariant 64-bit constant kept in a register pair (ptxas would otherwise turn the
-// rounding add into a carry chain of two more instructions per use).
-__device__ __forceinline__ uint64_t pinned_u64(uint64_t v)
-{
-    uint64_t r;
-    asm volatile("mov.u64 %0, %1;" : "=l"(r) : "l"(v));
-    return r;
-}
-// Roulette (reference photon.c:45-49) in five straight-line instructions.
-__device__ __forceinline__ void roulette_one(uint32_t& w, uint32_t& fate, uint32_t thr)
-{
-    asm("{\n"
-        " .reg .pred play, surv;\n"
-        " .reg .u32 m;\n"
-        " setp.lt.u32 play, %0, %2;\n"
-        " setp.lt.and.u32 surv, %1, %3, play;\n"
-        " selp.u32 m, 10, 0, surv;\n"
-        " @play mul.lo.u32 %0, %0, m;\n"
-        " @surv mul.lo.u32 %1, %1, 10;\n"
-        "}\n"
-        : "+r"(w), "+r"(fate)
-        : "r"(thr), "n"(kFateSurvive));
 }
 __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v)
 {
@@ -125,18 +116,74 @@ __device__ __forceinline__ uint32_t atom_shared_exch0(uint32_t addr)
     asm volatile("atom.shared.exch.b32 %0, [%1], 0;" : "=r"(r) : "r"(addr) : "memory");
     return r;
 }
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+    uint32_t r;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r));
+    return r;
+}
+
+template <bool V>
+struct BoolTag {
+    static constexpr bool value = V;
+};
+template <int V>
+struct IntTag {
+    static constexpr int value = V;
+};
+
+// Move slice `slice` (of BLOCK/32) of the block's u32 histograms into the global u64 tallies.
+// atomicExch: no barrier needed, the other warps keep adding meanwhile.  Called by a whole
+// converged warp; returns bit 0 set when a word had come within a factor two of wrapping.
+template <int BLOCK, bool LANE_PRIVATE>
+__device__ __noinline__ uint32_t drain_slice(uint32_t* bins, unsigned long long* tallies, uint32_t shells, uint32_t slice)
+{
+    constexpr uint32_t WARPS = BLOCK / 32;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t flag = 0u;
+    if constexpr (LANE_PRIVATE) {
+        const uint32_t rows = 2u * shells;             // row = shell * 2 + kind, 32 lanes wide
+        for (uint32_t row = slice; row < rows; row += WARPS) {
+            const uint32_t v = atomicExch(&bins[row * 32u + lane], 0u);
+            flag |= v >> 31;
+            if (__any_sync(0xffffffffu, v != 0u)) {
+                const uint32_t lo = __reduce_add_sync(0xffffffffu, v & 0xFFFFu);
+                const uint32_t hi = __reduce_add_sync(0xffffffffu, v >> 16);
+                if (lane == 0u)
+                    atomicAdd(&tallies[(row & 1u) * shells + (row >> 1)], (static_cast<unsigned long long>(hi) << 16) + lo);
+            }
+        }
+    } else {
+        const uint32_t plain_bins = shells + 31u;
+        for (uint32_t i = slice * 32u + lane; i < 2u * plain_bins; i += BLOCK) {
+            const uint32_t v = atomicExch(&bins[i], 0u);
+            if (v != 0u) {
+                flag |= v >> 31;
+                const uint32_t kind = i >= plain_bins ? 1u : 0u;
+                const uint32_t s = min(i - kind * plain_bins, shells - 1u);
+                atomicAdd(&tallies[kind * shells + s], static_cast<unsigned long long>(v));
+            }
+        }
+    }
+    return flag;
+}
 
 // LANE_PRIVATE: bins[shell][kind][lane] (u32), kind 0 = heat, 1 = heat2; else heat[shells+31] | heat2[shells+31]
 template <int ROUNDS, int BLOCK, int MIN_BLOCKS, bool LANE_PRIVATE>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __grid_constant__ WalkArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t drain_ticket;
+    constexpr uint32_t WARPS = BLOCK / 32;
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
+    const uint32_t wid = tid >> 5;
     const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
     const uint32_t bins_base = smem_base + kAzimuthBytes;
     const uint32_t plain_bins = a.shells + 31u;                              // per kind, plain layout
     const uint32_t nwords = LANE_PRIVATE ? a.shells * 64u : 2u * plain_bins;
+    // this warp's survivor queues: [generation 1|2][field][kQueueCap]
+    uint32_t* const queue = smem + kAzimuthBytes / 4u + nwords + wid * (kQueueBytesPerWarp / 4u);
 
     {   // stage the azimuth table and clear the histograms
         const float4* src = reinterpret_cast<const float4*>(a.azimuth);
@@ -144,6 +191,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
         for (uint32_t i = tid; i < kAzimuthEntries / 2; i += BLOCK) dst[i] = __ldg(src + i);
         uint32_t* bins = smem + kAzimuthBytes / 4u;
         for (uint32_t i = tid; i < nwords; i += BLOCK) bins[i] = 0u;
+        if (tid == 0u) drain_ticket = 0u;
     }
     __syncthreads();
 
@@ -154,169 +202,224 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     // plain layout: lane l clamps to slot SHELLS-1+l, so the overflow bin never serialises a warp
     const uint32_t clamp_bits = LANE_PRIVATE ? a.last_bits : a.last_bits + lane;
 
-    // static strided photon -> slot map: slot g owns photons first + g, first + g + stride, ...
-    // rel = photon index - first, signed so that "before the first photon" is representable.
-    const int32_t stride = static_cast<int32_t>(gridDim.x * (2u * BLOCK));
-    const int32_t rel_limit = static_cast<int32_t>(a.count) - stride;     // a successor exists iff rel < rel_limit
-    const uint32_t slot0 = (blockIdx.x * BLOCK + tid) * 2u;
-
-    int32_t rel[2];
-    uint32_t w[2], fate[2], blk[2];
-    float2 px, py, pz, dx, dy, dz;      // .x = photon A, .y = photon B  (reference photon.c:12-17)
-    px = py = pz = dx = dy = dz = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        rel[j] = static_cast<int32_t>(slot0 + j) - stride;   // the first regeneration steps onto slot0 + j
-        w[j] = 0u;                                           // 0 <=> no live photon in this slot
-        fate[j] = 0u;
-        blk[j] = 1u;
-    }
-    uint32_t n_events = 0u, range_flag = 0u;
-
     // Philox round 0 with the counter folded in: c0 = first_lo + rel, c1 = first_hi, c3 = 0.
     //   M0 * c0 = M0 * rel + M0 * first_lo   (no wrap: the launch stays inside one 2^32 window)
-    const uint32_t first_lo = static_cast<uint32_t>(a.first);
-    const uint64_t m0_first = static_cast<uint64_t>(kPhiloxM0) * first_lo;
+    const uint64_t m0_first = static_cast<uint64_t>(kPhiloxM0) * static_cast<uint32_t>(a.first);
     const uint32_t c1k0 = static_cast<uint32_t>(a.first >> 32) ^ a.keys.k[0];
 
-    const float2 half2 = make_float2(0.5f, 0.5f);
-    const float2 negln2 = make_float2(-kLn2, -kLn2);
-    const float2 bias2 = make_float2(kStepBias, kStepBias);
-    const float2 spm2 = make_float2(a.shells_per_mfp, a.shells_per_mfp);
-    const float2 magic2 = make_float2(8388608.0f, 8388608.0f);
-    const float2 two2 = make_float2(2.0f, 2.0f), ntwo2 = make_float2(-2.0f, -2.0f);
-    const float2 three2 = make_float2(3.0f, 3.0f), nthree2 = make_float2(-3.0f, -3.0f);
-    const float2 one2 = make_float2(1.0f, 1.0f);
-    const uint64_t round_half = pinned_u64(0x80000000ull);
-    const uint64_t heat2_half = pinned_u64(a.heat2_half);
+    // two photons per lane: position (mean-free-path units, photon.c:12-14), photon offset
+    // from a.first, roulette fate word, "this slot holds a photon"
+    float px[2], py[2], pz[2];
+    uint32_t rel[2], fate[2];
+    bool act[2], surv[2];
+    uint32_t r[2][4];                       // the current Philox block of each photon
 
-    // One scatter event for both photons of the thread: hop, drop (reference photon.c:21-32),
-    // branch-free.  A slot without a live photon has w == 0: it deposits 0.
-    auto scatter = [&](uint32_t wsA, uint32_t wsB) {
-        n_events += min(w[0], 1u) + min(w[1], 1u);
-        // hop: xi = (ws + 0.5) / 2^32, t = -ln(xi) = 32 ln2 - ln2 * lg2(ws + 0.5)
-        float2 u = __fadd2_rn(make_float2(__uint2float_rn(wsA), __uint2float_rn(wsB)), half2);
-        u.x = mufu_lg2(u.x);
-        u.y = mufu_lg2(u.y);
-        const float2 t = __ffma2_rn(u, negln2, bias2);
-        px = __ffma2_rn(t, dx, px);
-        py = __ffma2_rn(t, dy, py);
-        pz = __ffma2_rn(t, dz, pz);
-        // drop: shell = min(trunc(|r| * shells_per_mfp), SHELLS-1) without F2I: add 2^23 with
-        // round-toward-zero, clamp the raw bits, the mantissa is the integer.
-        float2 r2 = __ffma2_rn(pz, pz, __ffma2_rn(py, py, __fmul2_rn(px, px)));
-        r2.x = mufu_sqrt(r2.x);
-        r2.y = mufu_sqrt(r2.y);
-        const float2 sbf = __ffma2_rz(r2, spm2, magic2);
-        const uint32_t sbits[2] = { min(__float_as_uint(sbf.x), clamp_bits), min(__float_as_uint(sbf.y), clamp_bits) };
+    unsigned long long n_events = 0ull;     // warp-uniform
+    uint32_t range_flag = 0u;
+    uint32_t blocks_since_drain = 0u;       // warp-uniform
+
+    // Drain one slice (1 / WARPS) of the block histograms into the global u64 tallies.  Slices
+    // are handed out round-robin by a block-wide ticket, so every slice is drained once per
+    // WARPS calls no matter which warps are still walking (a warp that has run out of photons
+    // stops calling).  Out of line: the walk loop keeps its registers.
+    auto drain = [&]() {
+        uint32_t ticket = 0u;
+        if (lane == 0u) ticket = atomicAdd(&drain_ticket, 1u);
+        range_flag |= drain_slice<BLOCK, LANE_PRIVATE>(smem + kAzimuthBytes / 4u, a.tallies, a.shells,
+                                                       __shfl_sync(0xffffffffu, ticket, 0) % WARPS);
+    };
+
+    // One scatter event (reference photon.c:21-43) of slot S of the current Philox block for
+    // both photons of the lane: spin, hop, drop.  `dep` / `dep2` are the warp-uniform deposit
+    // (1-albedo) * w and its rescaled square.
+    auto event = [&](auto slot_tag, auto partial_tag, uint32_t dep, uint32_t dep2) {
+        constexpr int S = decltype(slot_tag)::value;
+        constexpr bool PARTIAL = decltype(partial_tag)::value;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            // deposit (1-albedo) * w, rounded: hi32(w * q32 + 2^31); its square, rescaled
-            const uint32_t dep = static_cast<uint32_t>(mad_wide(w[j], a.absorb_q32, round_half) >> 32);
-            const uint32_t dep2 = static_cast<uint32_t>(mad_wide(dep, dep, heat2_half) >> a.heat2_rshift);
-            w[j] -= dep;                                                          // w *= albedo
-            const uint32_t addr = (sbits[j] << SHIFT) + addr_bias;
-            red_shared_add(addr, dep);
-            red_shared_add(addr + heat2_off, dep2);
-        }
-    };
-    // roulette (reference photon.c:45-49).  The fate word is a uniform 32-bit integer drawn at
-    // birth; surviving (prob 0.1) multiplies it by 10, which is again uniform.  Death: w = 0.
-    auto roulette = [&]() {
-        roulette_one(w[0], fate[0], a.roulette_thr);
-        roulette_one(w[1], fate[1], a.roulette_thr);
-    };
-    // New isotropic direction from one 32-bit word per photon (replaces the rejection loop of
-    // reference photon.c:35-43): cos(theta) uniform from bits 9..31, azimuth from bits 3..14.
-    auto spin = [&](uint32_t wdA, uint32_t wdB) {
-        const float2 cf = make_float2(__uint_as_float(__funnelshift_r(wdA, 0x7Fu, 9)),    // 1 + m*2^-23 in [1,2)
-                                      __uint_as_float(__funnelshift_r(wdB, 0x7Fu, 9)));
-        const float2 ct = __ffma2_rn(cf, two2, nthree2);                                  // [-1, 1), exact
-        const float2 nct = __ffma2_rn(cf, ntwo2, three2);                                 // -ct, exact
-        float2 st = __ffma2_rn(ct, nct, one2);                                            // 1 - ct^2
-        st.x = mufu_sqrt(st.x);
-        st.y = mufu_sqrt(st.y);
-        const float2 csA = lds_f32x2(smem_base + (wdA & ((kAzimuthEntries - 1u) << 3)));
-        const float2 csB = lds_f32x2(smem_base + (wdB & ((kAzimuthEntries - 1u) << 3)));
-        dx = ct;
-        dy = make_float2(st.x * csA.x, st.y * csB.x);
-        dz = make_float2(st.x * csA.y, st.y * csB.y);
-    };
-    // Drain the block histograms into the global u64 tallies (atomicExch: no barrier needed,
-    // other warps keep adding).  Warp-uniform: every lane of the warp must be here.
-    auto drain = [&]() {
-        if constexpr (LANE_PRIVATE) {
-            const uint32_t rows = 2u * a.shells;           // row = shell * 2 + kind, 32 lanes wide
-            for (uint32_t r = tid >> 5; r < rows; r += BLOCK / 32) {
-                const uint32_t v = atom_shared_exch0(bins_base + (r * 32u + lane) * 4u);
-                range_flag |= v >> 31;
-                if (__any_sync(0xffffffffu, v != 0u)) {
-                    const uint32_t lo = __reduce_add_sync(0xffffffffu, v & 0xFFFFu);
-                    const uint32_t hi = __reduce_add_sync(0xffffffffu, v >> 16);
-                    if (lane == 0u)
-                        atomicAdd(&a.tallies[(r & 1u) * a.shells + (r >> 1)], (static_cast<unsigned long long>(hi) << 16) + lo);
-                }
-            }
-        } else {
-            for (uint32_t i = tid; i < nwords; i += BLOCK) {
-                const uint32_t v = atom_shared_exch0(bins_base + i * 4u);
-                if (v != 0u) {
-                    range_flag |= v >> 31;
-                    const uint32_t kind = i >= plain_bins ? 1u : 0u;
-                    const uint32_t s = min(i - kind * plain_bins, a.shells - 1u);
-                    atomicAdd(&a.tallies[kind * a.shells + s], static_cast<unsigned long long>(v));
-                }
+            const uint32_t v = r[j][S];
+            // spin: cos(theta) = (2k+1)/512 - 1 from bits 1..9 (exact), sin(theta) by MUFU.SQRT,
+            // azimuth (cos, sin) from the table, indexed by 10 bits of word 3
+            const float ct = fmaf(__uint_as_float((v & 0x3FEu) | 0x4B000001u), 0.001953125f, -16385.0f);
+            const float st = mufu_sqrt(fmaf(-ct, ct, 1.0f));
+            const uint32_t az = S == 0 ? (r[j][3] << 3) & 0x1FF8u : (r[j][3] >> (S == 1 ? 7 : 17)) & 0x1FF8u;
+            const float2 cs = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(smem) + az);
+            // hop: xi = 2 * (1.5 - f), f = 1 + (v >> 10) * 2^-23; t = -ln(xi)
+            const float f = __uint_as_float(__funnelshift_r(v, 0xFEu, 10));
+            const float t = fmaf(mufu_lg2(1.5f - f), -kLn2, -kLn2);
+            const float ts = t * st;
+            px[j] = fmaf(t, ct, px[j]);
+            py[j] = fmaf(ts, cs.x, py[j]);
+            pz[j] = fmaf(ts, cs.y, pz[j]);
+            // drop: shell = min(trunc(|r| * shells_per_mfp), SHELLS-1) without F2I: add 2^23 with
+            // round-toward-zero, clamp the raw bits, the mantissa is the integer.
+            const float rad = mufu_sqrt(fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j])));
+            const uint32_t sb = min(__float_as_uint(__fmaf_rz(rad, a.shells_per_mfp, 8388608.0f)), clamp_bits);
+            const uint32_t addr = (sb << SHIFT) + addr_bias;
+            if (!PARTIAL || act[j]) {
+                red_shared_add(addr, dep);
+                red_shared_add(addr + heat2_off, dep2);
             }
         }
     };
 
-    bool more = true;
-    while (more) {
-        for (uint32_t it = 0; it < a.flush_iters; ++it) {
-            uint32_t r[2][4];
-            bool born[2];
+    // Walk generation g for the photons held by the warp, then play roulette (photon.c:45-49).
+    auto phase = [&](auto partial_tag, uint32_t g) {
+        constexpr bool PARTIAL = decltype(partial_tag)::value;
+        const uint32_t ev_first = a.gen[g].first_event;
+        const uint32_t ev_last = ev_first + a.gen[g].n_events - 1u;
+        const uint32_t b_first = ev_first / 3u, b_last = ev_last / 3u;
+        // The warp-uniform weight schedule: event e deposits (1-albedo) * w(e), rounded, and its
+        // rescaled square; both come from a table the host computed with the exact integer
+        // recurrence (tmc_api.cu: deposit_table), one broadcast load per event.
+        const uint2* next_deposit = a.deposits + ev_first;
+        uint32_t dep = 0u, dep2 = 0u;
+        auto absorb = [&]() {
+            const uint2 d = __ldg(next_deposit++);
+            dep = d.x;
+            dep2 = d.y;
+        };
+        // one Philox block per photon: counter = (photon index, b)
+        auto draw = [&](uint32_t b) {
+            const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * b;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                born[j] = (w[j] == 0u) && (rel[j] < rel_limit);   // regenerate in place
-                if (born[j]) {
-                    rel[j] += stride;
-                    blk[j] = 0u;
-                }
-                const uint64_t p0 = mad_wide(static_cast<uint32_t>(rel[j]), kPhiloxM0, m0_first);
-                const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * blk[j];
+                const uint64_t p0 = mad_wide(rel[j], kPhiloxM0, m0_first);
                 philox4x32_rounds<1, ROUNDS>(a.keys, static_cast<uint32_t>(p1 >> 32) ^ c1k0, static_cast<uint32_t>(p1),
                                              static_cast<uint32_t>(p0 >> 32) ^ a.keys.k[1], static_cast<uint32_t>(p0), r[j]);
-                ++blk[j];
             }
-            // slot A.  In its birth block a photon still has w == 0, so the scatter deposits
-            // nothing; then it gets its weight, its fate word, the origin, and (from the spin
-            // of this slot) its launch direction.
-            scatter(r[0][0], r[1][0]);
-            if (born[0]) { w[0] = a.weight_one; fate[0] = r[0][0]; px.x = 0.0f; py.x = 0.0f; pz.x = 0.0f; }
-            if (born[1]) { w[1] = a.weight_one; fate[1] = r[1][0]; px.y = 0.0f; py.y = 0.0f; pz.y = 0.0f; }
-            roulette();
-            spin(r[0][1], r[1][1]);
-            // slot B
-            scatter(r[0][2], r[1][2]);
-            roulette();
-            spin(r[0][3], r[1][3]);
+        };
+        auto maybe_drain = [&]() {
+            if (++blocks_since_drain >= a.flush_blocks) {
+                drain();
+                blocks_since_drain = 0u;
+            }
+        };
+        // first / last block of the generation: only slots s_lo .. s_hi belong to it
+        auto ragged_block = [&](uint32_t b, uint32_t s_lo, uint32_t s_hi) {
+            draw(b);
+            if (b == 0u) {                       // pseudo-event 0: the fate word
+                fate[0] = r[0][0];
+                fate[1] = r[1][0];
+            }
+            if (s_lo == 0u) { absorb(); event(IntTag<0>{}, partial_tag, dep, dep2); }
+            if (s_lo <= 1u && s_hi >= 1u) { absorb(); event(IntTag<1>{}, partial_tag, dep, dep2); }
+            if (s_hi == 2u) { absorb(); event(IntTag<2>{}, partial_tag, dep, dep2); }
+            maybe_drain();
+        };
+        const uint32_t s_first = ev_first - 3u * b_first, s_last = ev_last - 3u * b_last;
+        if (b_first == b_last) {
+            ragged_block(b_first, s_first, s_last);
+        } else {
+            ragged_block(b_first, s_first, 2u);
+            for (uint32_t b = b_first + 1u; b < b_last; ++b) {
+                draw(b);
+                absorb();
+                event(IntTag<0>{}, partial_tag, dep, dep2);
+                absorb();
+                event(IntTag<1>{}, partial_tag, dep, dep2);
+                absorb();
+                event(IntTag<2>{}, partial_tag, dep, dep2);
+                maybe_drain();
+            }
+            ragged_block(b_last, 0u, s_last);
         }
-        drain();
-        more = __any_sync(0xffffffffu, (w[0] | w[1]) != 0u || rel[0] < rel_limit || rel[1] < rel_limit);
+        uint32_t n_act = 64u;
+        if constexpr (PARTIAL) n_act = __popc(__ballot_sync(0xffffffffu, act[0])) + __popc(__ballot_sync(0xffffffffu, act[1]));
+        n_events += static_cast<unsigned long long>(n_act) * a.gen[g].n_events;
+        // roulette: the fate word is a uniform 32-bit integer; surviving (probability 0.1)
+        // multiplies it by 10, which is uniform again.  The x10 weight boost is in gen[g+1].
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            surv[j] = (!PARTIAL || act[j]) && fate[j] < kFateSurvive;
+            if (surv[j]) fate[j] *= 10u;
+        }
+    };
+
+    // static cohort -> warp map: warp W owns cohorts W, W + total_warps, ... of 64 photons each
+    const uint32_t total_warps = gridDim.x * WARPS;
+    const uint32_t count = static_cast<uint32_t>(a.count);
+    const uint32_t n_cohorts = (count + 63u) / 64u;
+    uint32_t cohort = blockIdx.x * WARPS + wid;
+    uint32_t nq[2] = { 0u, 0u };            // fill of this warp's generation-1 and -2 queues
+
+    for (;;) {
+        uint32_t g, take;
+        if (nq[1] >= 64u) { g = 2u; take = 64u; }
+        else if (nq[0] >= 64u) { g = 1u; take = 64u; }
+        else if (cohort < n_cohorts) { g = 0u; take = min(64u, count - cohort * 64u); }
+        else if (nq[0] > 0u) { g = 1u; take = nq[0]; }
+        else if (nq[1] > 0u) { g = 2u; take = nq[1]; }
+        else break;
+
+        if (g == 0u) {                      // regenerate: 64 fresh photons at the origin
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                rel[j] = cohort * 64u + lane * 2u + j;
+                px[j] = py[j] = pz[j] = 0.0f;
+                fate[j] = 0u;
+                act[j] = lane * 2u + j < take;
+            }
+            cohort += total_warps;
+        } else {                            // a cohort of parked survivors of generation g
+            const uint32_t* q = queue + (g - 1u) * (kQueueFields * kQueueCap);
+            const uint32_t start = nq[g - 1u] - take;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t e = lane * 2u + j;
+                act[j] = e < take;
+                const uint32_t at = act[j] ? start + e : 0u;
+                px[j] = __uint_as_float(q[0u * kQueueCap + at]);
+                py[j] = __uint_as_float(q[1u * kQueueCap + at]);
+                pz[j] = __uint_as_float(q[2u * kQueueCap + at]);
+                rel[j] = q[3u * kQueueCap + at];
+                fate[j] = q[4u * kQueueCap + at];
+            }
+            __syncwarp();
+            nq[g - 1u] = start;
+        }
+
+        bool partial = take < 64u;
+        for (;;) {
+            if (partial) phase(BoolTag<true>{}, g);
+            else phase(BoolTag<false>{}, g);
+            if (g + 1u >= a.n_gen) break;
+            if (g + 1u <= 2u) {             // park the survivors for a later full cohort
+                uint32_t* q = queue + g * (kQueueFields * kQueueCap);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, surv[j]);
+                    const uint32_t at = nq[g] + __popc(m & lanemask_lt());
+                    if (surv[j]) {
+                        q[0u * kQueueCap + at] = __float_as_uint(px[j]);
+                        q[1u * kQueueCap + at] = __float_as_uint(py[j]);
+                        q[2u * kQueueCap + at] = __float_as_uint(pz[j]);
+                        q[3u * kQueueCap + at] = rel[j];
+                        q[4u * kQueueCap + at] = fate[j];
+                    }
+                    nq[g] += __popc(m);
+                }
+                __syncwarp();
+                break;
+            }
+            // deeper generations (1e-3 of the photons): the survivors continue in place
+            if (!__any_sync(0xffffffffu, surv[0] || surv[1])) break;
+            act[0] = surv[0];
+            act[1] = surv[1];
+            partial = true;
+            ++g;
+        }
     }
 
-    // Final drain once every thread of the block is done.
+    // Final drain once every warp of the block is done.
     __syncthreads();
-    drain();
-    unsigned long long ev = n_events;
+    range_flag |= drain_slice<BLOCK, LANE_PRIVATE>(smem + kAzimuthBytes / 4u, a.tallies, a.shells, wid);
     uint32_t fl = range_flag;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ev += __shfl_xor_sync(0xffffffffu, ev, o);
-        fl |= __shfl_xor_sync(0xffffffffu, fl, o);
-    }
+    for (int o = 16; o > 0; o >>= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);
     if (lane == 0u) {
-        atomicAdd(&a.counters[0], ev);
+        atomicAdd(&a.counters[0], n_events);
         if (fl) atomicOr(&a.counters[2], 1ull);
     }
     if (tid == 0u && blockIdx.x == 0u) atomicAdd(&a.counters[1], static_cast<unsigned long long>(a.count));

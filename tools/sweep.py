@@ -13,9 +13,9 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import tiny_mc_b200 as tmc  # noqa: E402
 
 PLANS = {
-    "default": dict(n=1 << 25, blocks=[128, 256, 512, 1024], per_sm=[0, 1, 2, 3], flush=[0, 64, 1024], rounds=[10, 7]),
-    "highalbedo": dict(n=1 << 19, blocks=[256, 512], per_sm=[0, 2], flush=[0, 64], rounds=[10]),
-    "finegrid": dict(n=1 << 25, blocks=[256, 512, 1024], per_sm=[0], flush=[0, 32, 512], rounds=[10]),
+    "default": dict(n=1 << 25, blocks=[128, 256, 512], per_sm=[0, 1, 2], flush=[0, 8], rounds=[10, 7]),
+    "highalbedo": dict(n=1 << 19, blocks=[256, 512], per_sm=[0, 2], flush=[0], rounds=[10]),
+    "finegrid": dict(n=1 << 25, blocks=[256, 512], per_sm=[0], flush=[0, 4], rounds=[10]),
 }
 
 
