@@ -39,8 +39,13 @@ template <int FIRST, int LAST>
 __device__ __forceinline__ void philox4x32_rounds(const PhiloxKeys& keys, uint32_t c0, uint32_t c1, uint32_t c2,
                                                   uint32_t c3, uint32_t (&out)[4])
 {
+#if defined(TMC_EXPERIMENT) && TMC_EXPERIMENT == 3   /* 3 rounds only (timing experiment) */
+    constexpr int LAST_ = FIRST + 2;
+#else
+    constexpr int LAST_ = LAST;
+#endif
 #pragma unroll
-    for (int r = FIRST; r < LAST; ++r) {
+    for (int r = FIRST; r < LAST_; ++r) {
         const uint64_t p0 = static_cast<uint64_t>(kPhiloxM0) * c0;  // IMAD.WIDE.U32
         const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;
         const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ keys.k[2 * r];      // LOP3

@@ -196,8 +196,7 @@ using KernelFn = void (*)(const WalkArgs);
 
 // Block shapes: threads per block (two photons per thread) x the residency the register
 // budget is compiled for.  A block needs 8 KB (azimuth table) + its tallies (SHELLS * 256 B
-// lane-private, else (SHELLS + 31) * 8 B) + 5 KB of survivor queues per warp: small grids run
-// three 256-thread blocks per SM, the plain layout (SHELLS > 512) one 512-thread block.
+// lane-private, else (SHELLS + 31) * 8 B) of shared memory.
 template <int ROUNDS, bool LANE_PRIVATE>
 KernelFn kernel_for_block(int block)
 {
@@ -224,6 +223,38 @@ KernelFn pick_kernel(int rounds, int block, bool lane_private)
 // (cos, sin)(2 pi i / 1024) in float, computed in double on the host and uploaded once per
 // device; every block stages it into shared memory (walk_kernel.cuh: spin()).
 const float2* g_azimuth[64] = {};
+
+// Survivor-queue scratch (walk_kernel.cuh): kQueueBytesPerWarp per warp of the largest grid, one
+// buffer per device and stream (two launches on one stream are ordered, so they can share it).
+struct QueueScratch {
+    int device;
+    cudaStream_t stream;
+    uint32_t* d_buf;
+    size_t bytes;
+};
+std::vector<QueueScratch> g_queue_scratch;
+
+int queue_scratch(int device, cudaStream_t stream, size_t bytes, uint32_t** out)
+{
+    for (QueueScratch& q : g_queue_scratch)
+        if (q.device == device && q.stream == stream) {
+            if (q.bytes < bytes) {
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                CUDA_TRY(cudaFree(q.d_buf));
+                q.d_buf = nullptr;
+                q.bytes = 0;
+                CUDA_TRY(cudaMalloc(&q.d_buf, bytes));
+                q.bytes = bytes;
+            }
+            *out = q.d_buf;
+            return TMC_OK;
+        }
+    uint32_t* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, bytes));
+    g_queue_scratch.push_back(QueueScratch{ device, stream, d, bytes });
+    *out = d;
+    return TMC_OK;
+}
 
 int azimuth_table(int device, const float2** out)
 {
@@ -386,6 +417,8 @@ int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t fi
         if (rc) return rc;
         if (!have_first && first_cfg) *first_cfg = cfg;
         have_first = true;
+        rc = queue_scratch(dev, stream, static_cast<size_t>(cfg.grid) * (cfg.block / 32) * tmc::kQueueBytesPerWarp, &a.queues);
+        if (rc) return rc;
         a.first = first;
         a.count = n;
         a.flush_blocks = cfg.flush_iters;

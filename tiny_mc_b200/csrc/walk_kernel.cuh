@@ -37,6 +37,10 @@
 
 #include "philox.cuh"
 
+#ifndef TMC_EXPERIMENT
+#define TMC_EXPERIMENT 0   /* timing experiments (tools/experiments.sh); the product is built with 0 */
+#endif
+
 namespace tmc {
 
 constexpr int kAzimuthEntries = 1024;                       // (cos, sin)(2 pi i / 1024): 8 KB
@@ -61,6 +65,7 @@ struct WalkArgs {
     unsigned long long* counters;   // global u64[4]: events, photons, range flag, -
     const float2* azimuth;          // global (cos, sin)(2 pi i / 1024)
     const uint2* deposits;          // global (deposit, rescaled deposit^2) of event e, e = 1 .. last event of gen[n_gen-1]
+    uint32_t* queues;               // global scratch: kQueueBytesPerWarp per warp of the grid (survivor queues)
     float shells_per_mfp;           // reference photon.c:9
     uint32_t shells;                // SHELLS (reference params.h:5)
     uint32_t last_bits;             // 0x4B000000 + SHELLS-1 : clamp in the magic-number domain
@@ -76,7 +81,8 @@ constexpr float kLn2 = 0.693147182464599609375f;
 // shared-memory bytes of one block
 inline uint32_t walk_smem_bytes(uint32_t shells, bool lane_private, uint32_t block_threads)
 {
-    return kAzimuthBytes + (lane_private ? shells * 256u : 2u * (shells + 31u) * 4u) + (block_threads / 32u) * kQueueBytesPerWarp;
+    (void)block_threads;
+    return kAzimuthBytes + (lane_private ? shells * 256u : 2u * (shells + 31u) * 4u);
 }
 
 #ifdef __CUDACC__
@@ -100,14 +106,18 @@ __device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
     return r;
 }
+// No "memory" clobber: the histograms are touched by these atomics and by drain_slice (an
+// out-of-line call) only, so the compiler stays free to hoist the next event's table look-up
+// and arithmetic above the atomics of this one.
 __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v)
 {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v));
 }
+// The azimuth table is read-only after the block's first barrier: a pure function of the address.
 __device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
 {
     float2 r;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
     return r;
 }
 __device__ __forceinline__ uint32_t atom_shared_exch0(uint32_t addr)
@@ -182,8 +192,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     const uint32_t bins_base = smem_base + kAzimuthBytes;
     const uint32_t plain_bins = a.shells + 31u;                              // per kind, plain layout
     const uint32_t nwords = LANE_PRIVATE ? a.shells * 64u : 2u * plain_bins;
-    // this warp's survivor queues: [generation 1|2][field][kQueueCap]
-    uint32_t* const queue = smem + kAzimuthBytes / 4u + nwords + wid * (kQueueBytesPerWarp / 4u);
+    // this warp's survivor queues: [generation 1|2][field][kQueueCap], in global memory (a few
+    // accesses per cohort; L2-resident), so that shared memory holds only the table and tallies
+    uint32_t* const queue = a.queues + static_cast<size_t>(blockIdx.x * WARPS + wid) * (kQueueBytesPerWarp / 4u);
 
     {   // stage the azimuth table and clear the histograms
         const float4* src = reinterpret_cast<const float4*>(a.azimuth);
@@ -209,10 +220,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
 
     // two photons per lane: position (mean-free-path units, photon.c:12-14), photon offset
     // from a.first, roulette fate word, "this slot holds a photon"
-    float px[2], py[2], pz[2];
+    float2 px;                              // x of both photons, packed
+    float py[2], pz[2];
     uint32_t rel[2], fate[2];
     bool act[2], surv[2];
     uint32_t r[2][4];                       // the current Philox block of each photon
+    uint32_t rn[2][4];                      // the next one, drawn while the current block's events run
 
     unsigned long long n_events = 0ull;     // warp-uniform
     uint32_t range_flag = 0u;
@@ -235,31 +248,56 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     auto event = [&](auto slot_tag, auto partial_tag, uint32_t dep, uint32_t dep2) {
         constexpr int S = decltype(slot_tag)::value;
         constexpr bool PARTIAL = decltype(partial_tag)::value;
+        // The two photons of the lane are one packed FP32 pair wherever both need the same
+        // operation (Blackwell FFMA2 / FMUL2 / FADD2: two results per issue slot); .x = photon 0.
+        const uint32_t v0 = r[0][S], v1 = r[1][S];
+        // spin: cos(theta) = (2k+1)/512 - 1 from bits 1..9 (exact), sin(theta) by MUFU.SQRT,
+        // azimuth (cos, sin) from the table, indexed by 10 bits of word 3
+        const float2 ct = __ffma2_rn(make_float2(__uint_as_float((v0 & 0x3FEu) | 0x4B000001u), __uint_as_float((v1 & 0x3FEu) | 0x4B000001u)),
+                                     make_float2(0.001953125f, 0.001953125f), make_float2(-16385.0f, -16385.0f));
+        float2 st = __ffma2_rn(make_float2(-ct.x, -ct.y), ct, make_float2(1.0f, 1.0f));
+        st.x = mufu_sqrt(st.x);
+        st.y = mufu_sqrt(st.y);
+        const uint32_t az0 = S == 0 ? (r[0][3] << 3) & 0x1FF8u : (r[0][3] >> (S == 1 ? 7 : 17)) & 0x1FF8u;
+        const uint32_t az1 = S == 0 ? (r[1][3] << 3) & 0x1FF8u : (r[1][3] >> (S == 1 ? 7 : 17)) & 0x1FF8u;
+#if TMC_EXPERIMENT == 2   /* conflict-free table address (wrong physics; timing experiment only) */
+        const float2 cs0 = lds_f32x2(smem_base + ((az0 & 0x1F00u) | (lane << 3)));
+        const float2 cs1 = lds_f32x2(smem_base + ((az1 & 0x1F00u) | (lane << 3)));
+#else
+        const float2 cs0 = lds_f32x2(smem_base + az0);
+        const float2 cs1 = lds_f32x2(smem_base + az1);
+#endif
+        // hop: xi = 2 * (1.5 - f), f = 1 + (v >> 10) * 2^-23; t = -ln(xi)
+        const float2 f = make_float2(__uint_as_float(__funnelshift_r(v0, 0xFEu, 10)), __uint_as_float(__funnelshift_r(v1, 0xFEu, 10)));
+        float2 lg = __fadd2_rn(make_float2(-f.x, -f.y), make_float2(1.5f, 1.5f));
+        lg.x = mufu_lg2(lg.x);
+        lg.y = mufu_lg2(lg.y);
+        const float2 t = __ffma2_rn(lg, make_float2(-kLn2, -kLn2), make_float2(-kLn2, -kLn2));
+        const float2 ts = __fmul2_rn(t, st);
+        px = __ffma2_rn(t, ct, px);
+        py[0] = fmaf(ts.x, cs0.x, py[0]);
+        pz[0] = fmaf(ts.x, cs0.y, pz[0]);
+        py[1] = fmaf(ts.y, cs1.x, py[1]);
+        pz[1] = fmaf(ts.y, cs1.y, pz[1]);
+        // drop: shell = min(trunc(|r| * shells_per_mfp), SHELLS-1) without F2I: add 2^23 with
+        // round-toward-zero, clamp the raw bits, the mantissa is the integer.
+        const float2 xx = __fmul2_rn(px, px);
+        float2 rad;
+        rad.x = mufu_sqrt(fmaf(pz[0], pz[0], fmaf(py[0], py[0], xx.x)));
+        rad.y = mufu_sqrt(fmaf(pz[1], pz[1], fmaf(py[1], py[1], xx.y)));
+        const float2 sbf = __ffma2_rz(rad, make_float2(a.shells_per_mfp, a.shells_per_mfp), make_float2(8388608.0f, 8388608.0f));
+        const uint32_t sb[2] = { min(__float_as_uint(sbf.x), clamp_bits), min(__float_as_uint(sbf.y), clamp_bits) };
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const uint32_t v = r[j][S];
-            // spin: cos(theta) = (2k+1)/512 - 1 from bits 1..9 (exact), sin(theta) by MUFU.SQRT,
-            // azimuth (cos, sin) from the table, indexed by 10 bits of word 3
-            const float ct = fmaf(__uint_as_float((v & 0x3FEu) | 0x4B000001u), 0.001953125f, -16385.0f);
-            const float st = mufu_sqrt(fmaf(-ct, ct, 1.0f));
-            const uint32_t az = S == 0 ? (r[j][3] << 3) & 0x1FF8u : (r[j][3] >> (S == 1 ? 7 : 17)) & 0x1FF8u;
-            const float2 cs = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(smem) + az);
-            // hop: xi = 2 * (1.5 - f), f = 1 + (v >> 10) * 2^-23; t = -ln(xi)
-            const float f = __uint_as_float(__funnelshift_r(v, 0xFEu, 10));
-            const float t = fmaf(mufu_lg2(1.5f - f), -kLn2, -kLn2);
-            const float ts = t * st;
-            px[j] = fmaf(t, ct, px[j]);
-            py[j] = fmaf(ts, cs.x, py[j]);
-            pz[j] = fmaf(ts, cs.y, pz[j]);
-            // drop: shell = min(trunc(|r| * shells_per_mfp), SHELLS-1) without F2I: add 2^23 with
-            // round-toward-zero, clamp the raw bits, the mantissa is the integer.
-            const float rad = mufu_sqrt(fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j])));
-            const uint32_t sb = min(__float_as_uint(__fmaf_rz(rad, a.shells_per_mfp, 8388608.0f)), clamp_bits);
-            const uint32_t addr = (sb << SHIFT) + addr_bias;
+            const uint32_t addr = (sb[j] << SHIFT) + addr_bias;
+#if TMC_EXPERIMENT == 1   /* one atomic instead of two (timing experiment only) */
+            if (!PARTIAL || act[j]) red_shared_add(addr, dep + dep2);
+#else
             if (!PARTIAL || act[j]) {
                 red_shared_add(addr, dep);
                 red_shared_add(addr + heat2_off, dep2);
             }
+#endif
         }
     };
 
@@ -279,15 +317,24 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             dep = d.x;
             dep2 = d.y;
         };
-        // one Philox block per photon: counter = (photon index, b)
-        auto draw = [&](uint32_t b) {
+        // One Philox block per photon, counter = (photon index, b), into `out`.  The walk loop
+        // draws block b+1 while the events of block b run: the Philox rounds (IMAD.WIDE on the
+        // FMA-heavy pipe, LOP3) and the event arithmetic (FP32, MUFU, shared memory) use
+        // different pipes and have no data dependence, so ptxas interleaves them.
+        auto draw = [&](uint32_t b, uint32_t (&out)[2][4]) {
             const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * b;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const uint64_t p0 = mad_wide(rel[j], kPhiloxM0, m0_first);
                 philox4x32_rounds<1, ROUNDS>(a.keys, static_cast<uint32_t>(p1 >> 32) ^ c1k0, static_cast<uint32_t>(p1),
-                                             static_cast<uint32_t>(p0 >> 32) ^ a.keys.k[1], static_cast<uint32_t>(p0), r[j]);
+                                             static_cast<uint32_t>(p0 >> 32) ^ a.keys.k[1], static_cast<uint32_t>(p0), out[j]);
             }
+        };
+        auto advance = [&]() {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r[j][k] = rn[j][k];
         };
         auto maybe_drain = [&]() {
             if (++blocks_since_drain >= a.flush_blocks) {
@@ -295,9 +342,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                 blocks_since_drain = 0u;
             }
         };
-        // first / last block of the generation: only slots s_lo .. s_hi belong to it
+        // first / last block of the generation (already in r): only slots s_lo .. s_hi belong to it
         auto ragged_block = [&](uint32_t b, uint32_t s_lo, uint32_t s_hi) {
-            draw(b);
             if (b == 0u) {                       // pseudo-event 0: the fate word
                 fate[0] = r[0][0];
                 fate[1] = r[1][0];
@@ -308,18 +354,22 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             maybe_drain();
         };
         const uint32_t s_first = ev_first - 3u * b_first, s_last = ev_last - 3u * b_last;
+        draw(b_first, r);
         if (b_first == b_last) {
             ragged_block(b_first, s_first, s_last);
         } else {
+            draw(b_first + 1u, rn);
             ragged_block(b_first, s_first, 2u);
+            advance();
             for (uint32_t b = b_first + 1u; b < b_last; ++b) {
-                draw(b);
+                draw(b + 1u, rn);
                 absorb();
                 event(IntTag<0>{}, partial_tag, dep, dep2);
                 absorb();
                 event(IntTag<1>{}, partial_tag, dep, dep2);
                 absorb();
                 event(IntTag<2>{}, partial_tag, dep, dep2);
+                advance();
                 maybe_drain();
             }
             ragged_block(b_last, 0u, s_last);
@@ -356,10 +406,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 rel[j] = cohort * 64u + lane * 2u + j;
-                px[j] = py[j] = pz[j] = 0.0f;
+                py[j] = pz[j] = 0.0f;
                 fate[j] = 0u;
                 act[j] = lane * 2u + j < take;
             }
+            px = make_float2(0.0f, 0.0f);
             cohort += total_warps;
         } else {                            // a cohort of parked survivors of generation g
             const uint32_t* q = queue + (g - 1u) * (kQueueFields * kQueueCap);
@@ -370,7 +421,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                 const uint32_t e = lane * 2u + j;
                 act[j] = e < take;
                 const uint32_t at = act[j] ? start + e : 0u;
-                px[j] = __uint_as_float(q[0u * kQueueCap + at]);
+                (j == 0 ? px.x : px.y) = __uint_as_float(q[0u * kQueueCap + at]);
                 py[j] = __uint_as_float(q[1u * kQueueCap + at]);
                 pz[j] = __uint_as_float(q[2u * kQueueCap + at]);
                 rel[j] = q[3u * kQueueCap + at];
@@ -392,7 +443,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                     const uint32_t m = __ballot_sync(0xffffffffu, surv[j]);
                     const uint32_t at = nq[g] + __popc(m & lanemask_lt());
                     if (surv[j]) {
-                        q[0u * kQueueCap + at] = __float_as_uint(px[j]);
+                        q[0u * kQueueCap + at] = __float_as_uint(j == 0 ? px.x : px.y);
                         q[1u * kQueueCap + at] = __float_as_uint(py[j]);
                         q[2u * kQueueCap + at] = __float_as_uint(pz[j]);
                         q[3u * kQueueCap + at] = rel[j];

@@ -25,6 +25,8 @@ ncu)
 microncu)
   timeout 900 ncu --metrics sm__cycles_elapsed.avg,smsp__inst_executed.sum,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,sm__issue_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum \
       --clock-control none --csv --log-file gpurun_out/micro_ncu.csv tiny_mc_b200/bin/tmc_microbench > gpurun_out/micro_under_ncu.jsonl 2>&1; echo "microncu rc=$?" ;;
+quick)
+  timeout 600 python tools/quick_bench.py > gpurun_out/quick.jsonl 2> gpurun_out/quick.err; echo "quick rc=$?"; cat gpurun_out/quick.jsonl ;;
 sweep)
   timeout 900 python tools/sweep.py > gpurun_out/sweep.jsonl 2> gpurun_out/sweep.err; echo "sweep rc=$?" ;;
 esac
