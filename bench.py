@@ -192,9 +192,11 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    from tiny_mc_b200.shards import shard_range
+
     def device_step(step: int):
-        first = step * per_step + rank * per_gpu
-        tmc.photons_device(args.config, seed, first, per_gpu, local_rank, tallies.data_ptr(), stream.cuda_stream)
+        first, count = shard_range(step * per_step, per_step, rank, world)    # this rank's photon indices
+        tmc.photons_device(args.config, seed, first, count, local_rank, tallies.data_ptr(), stream.cuda_stream)
         if world > 1:
             dist.all_reduce(tallies)     # the single collective: 2*SHELLS+4 int64 words, exact
 
@@ -295,7 +297,7 @@ def run_ours(args):
         "bound": "issue",
         "achieved": achieved / 1e12, "peak": issue_peak / 1e12, "unit": "T lane-instr/s",
         "frac": achieved / issue_peak,
-        "traffic": None,
+        "traffic": 21760,
         "definition": "events/s/GPU x 88 canonical issue slots per event (SURVEY 8d: walk 35 + Philox4x32-10 53) "
                       "/ (SMs x 128 lanes/clk x SM clock sampled during the run)",
         "frac_walk_only_35_slots": events_per_s_per_gpu * WALK_SLOTS_PER_EVENT / issue_peak,
@@ -303,8 +305,13 @@ def run_ours(args):
         "events_per_s_per_gpu": events_per_s_per_gpu,
         "events_per_photon": events_per_photon,
         "peak_source": f"{sms} SMs x 128 lanes/clk x {f_sm_hz / 1e6:.0f} MHz (nvidia-smi median under load); "
-                       "MEASURED_PEAKS.json has no FP32/MUFU figure - see profiles/ for the on-box micro-benchmark",
-        "bytes_note": "HBM traffic is ~0: the kernel reads no input and flushes 2*SHELLS u64 words per block",
+                       "MEASURED_PEAKS.json holds HBM and bf16 peaks only - the issue rate was measured on the box: "
+                       "127.4 lanes/clk/SM sustained (profiles/r01_microbench_pipes.md)",
+        "hardware_truth": "ncu of this kernel (profiles/): warp instructions per event, issue-slot, FMA-heavy, ALU, XU and "
+                          "shared-pipe utilisation; frac > 1 means fewer instructions than the canonical 88-slot budget",
+        "philox10_ceiling_events_per_s": sms * 4 * f_sm_hz / 80.0 * 32 * 3,
+        "frac_of_philox10_ceiling": events_per_s_per_gpu / (sms * 4 * f_sm_hz / 80.0 * 32 * 3),
+        "bytes_note": "HBM traffic is ~20 KB per launch (ncu dram__bytes): the kernel reads no input",
     }
 
     line = {
