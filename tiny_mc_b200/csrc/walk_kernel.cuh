@@ -182,7 +182,7 @@ __device__ __noinline__ uint32_t drain_slice(uint32_t* bins, unsigned long long*
 template <int ROUNDS, int BLOCK, int MIN_BLOCKS, bool LANE_PRIVATE>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __grid_constant__ WalkArgs a)
 {
-    extern __shared__ __align__(16) uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];     // [azimuth table 8 KB | histograms]
     __shared__ uint32_t drain_ticket;
     constexpr uint32_t WARPS = BLOCK / 32;
     const uint32_t tid = threadIdx.x;
@@ -224,8 +224,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     float py[2], pz[2];
     uint32_t rel[2], fate[2];
     bool act[2], surv[2];
-    uint32_t r[2][4];                       // the current Philox block of each photon
-    uint32_t rn[2][4];                      // the next one, drawn while the current block's events run
+    uint32_t r[2][4];                       // the Philox block of each photon whose events are running
 
     unsigned long long n_events = 0ull;     // warp-uniform
     uint32_t range_flag = 0u;
@@ -264,8 +263,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
         const float2 cs0 = lds_f32x2(smem_base + ((az0 & 0x1F00u) | (lane << 3)));
         const float2 cs1 = lds_f32x2(smem_base + ((az1 & 0x1F00u) | (lane << 3)));
 #else
-        const float2 cs0 = lds_f32x2(smem_base + az0);
-        const float2 cs1 = lds_f32x2(smem_base + az1);
+        const float2 cs0 = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(smem) + az0);
+        const float2 cs1 = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(smem) + az1);
 #endif
         // hop: xi = 2 * (1.5 - f), f = 1 + (v >> 10) * 2^-23; t = -ln(xi)
         const float2 f = make_float2(__uint_as_float(__funnelshift_r(v0, 0xFEu, 10)), __uint_as_float(__funnelshift_r(v1, 0xFEu, 10)));
@@ -330,20 +329,31 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                                              static_cast<uint32_t>(p0 >> 32) ^ a.keys.k[1], static_cast<uint32_t>(p0), out[j]);
             }
         };
-        auto advance = [&]() {
+        auto three_events = [&](uint32_t (&cur)[2][4]) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) r[j][k] = rn[j][k];
+                for (int k = 0; k < 4; ++k) r[j][k] = cur[j][k];
+            absorb();
+            event(IntTag<0>{}, partial_tag, dep, dep2);
+            absorb();
+            event(IntTag<1>{}, partial_tag, dep, dep2);
+            absorb();
+            event(IntTag<2>{}, partial_tag, dep, dep2);
         };
-        auto maybe_drain = [&]() {
-            if (++blocks_since_drain >= a.flush_blocks) {
+        auto maybe_drain = [&](uint32_t blocks) {
+            blocks_since_drain += blocks;
+            if (blocks_since_drain >= a.flush_blocks) {
                 drain();
                 blocks_since_drain = 0u;
             }
         };
-        // first / last block of the generation (already in r): only slots s_lo .. s_hi belong to it
-        auto ragged_block = [&](uint32_t b, uint32_t s_lo, uint32_t s_hi) {
+        // first / last block of the generation (in `cur`): only slots s_lo .. s_hi belong to it
+        auto ragged_block = [&](uint32_t b, uint32_t (&cur)[2][4], uint32_t s_lo, uint32_t s_hi) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r[j][k] = cur[j][k];
             if (b == 0u) {                       // pseudo-event 0: the fate word
                 fate[0] = r[0][0];
                 fate[1] = r[1][0];
@@ -351,28 +361,40 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             if (s_lo == 0u) { absorb(); event(IntTag<0>{}, partial_tag, dep, dep2); }
             if (s_lo <= 1u && s_hi >= 1u) { absorb(); event(IntTag<1>{}, partial_tag, dep, dep2); }
             if (s_hi == 2u) { absorb(); event(IntTag<2>{}, partial_tag, dep, dep2); }
-            maybe_drain();
+            maybe_drain(1u);
         };
         const uint32_t s_first = ev_first - 3u * b_first, s_last = ev_last - 3u * b_last;
-        draw(b_first, r);
+        uint32_t ra[2][4], rb[2][4];            // ping-pong: the block being walked / the next one
+        draw(b_first, ra);
         if (b_first == b_last) {
-            ragged_block(b_first, s_first, s_last);
+            ragged_block(b_first, ra, s_first, s_last);
         } else {
-            draw(b_first + 1u, rn);
-            ragged_block(b_first, s_first, 2u);
-            advance();
-            for (uint32_t b = b_first + 1u; b < b_last; ++b) {
-                draw(b + 1u, rn);
-                absorb();
-                event(IntTag<0>{}, partial_tag, dep, dep2);
-                absorb();
-                event(IntTag<1>{}, partial_tag, dep, dep2);
-                absorb();
-                event(IntTag<2>{}, partial_tag, dep, dep2);
-                advance();
-                maybe_drain();
+            draw(b_first + 1u, rb);
+            ragged_block(b_first, ra, s_first, 2u);
+            // full blocks b_first+1 .. b_last-1, the current one in rb.  Chunks of at most
+            // flush_blocks blocks run without a call, so the Philox keys stay in uniform registers.
+            uint32_t b = b_first + 1u;
+            while (b < b_last) {
+                uint32_t chunk = min(b_last - b, a.flush_blocks - min(blocks_since_drain, a.flush_blocks - 1u));
+                const uint32_t done = chunk;
+                for (; chunk >= 2u; chunk -= 2u, b += 2u) {
+                    draw(b + 1u, ra);
+                    three_events(rb);
+                    draw(b + 2u, rb);
+                    three_events(ra);
+                }
+                if (chunk) {
+                    draw(b + 1u, ra);
+                    three_events(rb);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) rb[j][k] = ra[j][k];
+                    ++b;
+                }
+                maybe_drain(done);
             }
-            ragged_block(b_last, 0u, s_last);
+            ragged_block(b_last, rb, 0u, s_last);
         }
         uint32_t n_act = 64u;
         if constexpr (PARTIAL) n_act = __popc(__ballot_sync(0xffffffffu, act[0])) + __popc(__ballot_sync(0xffffffffu, act[1]));
