@@ -71,7 +71,7 @@ def test_argument_validation(tmc):
         assert lib.tmc_fx_scales(C.byref(p), C.byref(s)) == 2
         assert lib.tmc_last_error()
     assert lib.tmc_fx_scales(None, C.byref(s)) == 2
-    assert lib.tmc_set_option(b"philox_rounds", 6) == 2
+    assert lib.tmc_set_option(b"philox_rounds", 8) == 2
     assert lib.tmc_set_option(b"no_such_option", 1) == 2
     assert lib.tmc_set_option(b"philox_rounds", 10) == 0
     assert lib.tmc_last_run_info(None) == 2

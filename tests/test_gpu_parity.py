@@ -45,7 +45,7 @@ def test_gpu_equals_cpu_replay_of_the_same_stream(gpu, orc, name, n, flip_tol):
     assert info.retries == 0
 
 
-@pytest.mark.parametrize("rounds", [7, 8, 9, 10])
+@pytest.mark.parametrize("rounds", [7, 10])
 def test_philox_round_variants_match_replay(gpu, orc, rounds):
     gpu.set_option("philox_rounds", rounds)
     try:

@@ -198,25 +198,38 @@ using KernelFn = void (*)(const WalkArgs);
 // budget is compiled for.  A block needs 8 KB (azimuth table) + its tallies (SHELLS * 256 B
 // lane-private, else (SHELLS + 31) * 8 B) of shared memory.
 template <int ROUNDS, bool LANE_PRIVATE>
-KernelFn kernel_for_block(int block)
+KernelFn kernel_for_block(int block, int per_sm)
 {
-    switch (block) {
-    case 128: return tmc::photon_walk_kernel<ROUNDS, 128, 4, LANE_PRIVATE>;
-    case 256: return tmc::photon_walk_kernel<ROUNDS, 256, 3, LANE_PRIVATE>;
-    case 512: return tmc::photon_walk_kernel<ROUNDS, 512, 1, LANE_PRIVATE>;
-    case 1024: return tmc::photon_walk_kernel<ROUNDS, 1024, 1, LANE_PRIVATE>;
+    // (threads per block, blocks per SM the register budget is compiled for)
+    switch (block * 8 + per_sm) {
+    case 128 * 8 + 4: return tmc::photon_walk_kernel<ROUNDS, 128, 4, LANE_PRIVATE>;   // 128 registers
+    case 256 * 8 + 2: return tmc::photon_walk_kernel<ROUNDS, 256, 2, LANE_PRIVATE>;   // 128
+    case 256 * 8 + 3: return tmc::photon_walk_kernel<ROUNDS, 256, 3, LANE_PRIVATE>;   //  80
+    case 256 * 8 + 4: return tmc::photon_walk_kernel<ROUNDS, 256, 4, LANE_PRIVATE>;   //  64
+    case 512 * 8 + 1: return tmc::photon_walk_kernel<ROUNDS, 512, 1, LANE_PRIVATE>;   // 128
+    case 512 * 8 + 2: return tmc::photon_walk_kernel<ROUNDS, 512, 2, LANE_PRIVATE>;   //  64
+    case 1024 * 8 + 1: return tmc::photon_walk_kernel<ROUNDS, 1024, 1, LANE_PRIVATE>; //  64
     default: return nullptr;
     }
 }
 
-KernelFn pick_kernel(int rounds, int block, bool lane_private)
+KernelFn pick_kernel(int rounds, int block, int per_sm, bool lane_private)
 {
     switch (rounds) {
-    case 7: return lane_private ? kernel_for_block<7, true>(block) : kernel_for_block<7, false>(block);
-    case 8: return lane_private ? kernel_for_block<8, true>(block) : kernel_for_block<8, false>(block);
-    case 9: return lane_private ? kernel_for_block<9, true>(block) : kernel_for_block<9, false>(block);
-    case 10: return lane_private ? kernel_for_block<10, true>(block) : kernel_for_block<10, false>(block);
+    case 7: return lane_private ? kernel_for_block<7, true>(block, per_sm) : kernel_for_block<7, false>(block, per_sm);
+    case 10: return lane_private ? kernel_for_block<10, true>(block, per_sm) : kernel_for_block<10, false>(block, per_sm);
     default: return nullptr;
+    }
+}
+
+// the register budgets (blocks per SM) compiled for each block size, best first
+int default_blocks_per_sm(int block)
+{
+    switch (block) {
+    case 128: return 4;
+    case 256: return 2;
+    case 512: return 1;
+    default: return 1;
     }
 }
 
@@ -343,12 +356,18 @@ int configure_launch(const tmc_params* p, int device_sms, uint64_t count, uint32
     if (g.opt.tally_layout == 2 && !lane_private)
         return fail(TMC_ERR_BAD_ARG, "SHELLS=%u is too large for lane-private tallies (max %u)", p->shells, tmc::kLanePrivateMaxShells);
     int block = g.opt.block_threads;
-    if (block == 0) block = lane_private ? 256 : 512;
+    if (block == 0) block = lane_private ? 512 : 1024;   // measured best: profiles/r01_*sweep*
     const size_t smem = tmc::walk_smem_bytes(p->shells, lane_private, static_cast<uint32_t>(block));
     if (smem > 227u * 1024u)
         return fail(TMC_ERR_BAD_ARG, "SHELLS=%u with %d-thread blocks needs %zu B of shared memory per block (> 227 KB)", p->shells, block, smem);
-    KernelFn fn = pick_kernel(g.opt.philox_rounds, block, lane_private);
-    if (!fn) return fail(TMC_ERR_BAD_ARG, "no kernel for philox_rounds=%d block_threads=%d", g.opt.philox_rounds, block);
+    // register budget: the variant compiled for `want` resident blocks (fewer if shared memory says so)
+    int want = g.opt.blocks_per_sm > 0 ? g.opt.blocks_per_sm : default_blocks_per_sm(block);
+    const int smem_fit = static_cast<int>((227u * 1024u) / (smem + 1024u));
+    if (want > smem_fit) want = smem_fit;
+    KernelFn fn = nullptr;
+    for (int c = want; c >= 1 && !fn; --c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private);   // largest budget <= want
+    for (int c = want + 1; c <= 4 && !fn; ++c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private);   // else the next one
+    if (!fn) return fail(TMC_ERR_BAD_ARG, "no kernel for philox_rounds=%d block_threads=%d blocks_per_sm=%d", g.opt.philox_rounds, block, g.opt.blocks_per_sm);
     int per_sm = 0;
     int orc = kernel_occupancy(fn, block, smem, &per_sm);
     if (orc) return orc;
@@ -663,14 +682,14 @@ int tmc_set_option(const char* name, long long value)
     const std::string n(name);
     if (n == "philox_rounds") {
         if (value == 0) value = 10;
-        if (value < 7 || value > 10) return fail(TMC_ERR_BAD_ARG, "philox_rounds must be 7..10");
+        if (value != 7 && value != 10) return fail(TMC_ERR_BAD_ARG, "philox_rounds must be 10 (default) or 7");
         g.opt.philox_rounds = static_cast<int>(value);
     } else if (n == "block_threads") {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024)
             return fail(TMC_ERR_BAD_ARG, "block_threads must be 0, 128, 256, 512 or 1024");
         g.opt.block_threads = static_cast<int>(value);
     } else if (n == "blocks_per_sm") {
-        if (value < 0 || value > 32) return fail(TMC_ERR_BAD_ARG, "blocks_per_sm must be 0..32");
+        if (value < 0 || value > 4) return fail(TMC_ERR_BAD_ARG, "blocks_per_sm must be 0..4");
         g.opt.blocks_per_sm = static_cast<int>(value);
     } else if (n == "flush_iters") {
         if (value < 0 || value > 4096) return fail(TMC_ERR_BAD_ARG, "flush_iters must be 0..4096");

@@ -8,11 +8,16 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import tiny_mc_b200 as tmc  # noqa: E402
 
 tmc.init(1)
-plans = [("default", 1 << 26, 10, 0), ("default", 1 << 26, 7, 0), ("default", 1 << 26, 10, 512), ("default", 1 << 26, 7, 512),
-         ("highalbedo", 1 << 20, 10, 0), ("finegrid", 1 << 26, 10, 0)]
-for name, n, rounds, block in plans:
+plans = [("default", 1 << 26, 10, 0, 0), ("default", 1 << 26, 7, 0, 0), ("default", 1 << 26, 10, 256, 2), ("default", 1 << 26, 10, 256, 3),
+         ("default", 1 << 26, 10, 256, 4), ("default", 1 << 26, 10, 512, 1), ("default", 1 << 26, 10, 512, 2), ("default", 1 << 26, 10, 1024, 1),
+         ("default", 1 << 26, 10, 128, 4), ("highalbedo", 1 << 20, 10, 0, 0), ("highalbedo", 1 << 20, 10, 1024, 1), ("finegrid", 1 << 26, 10, 0, 0),
+         ("finegrid", 1 << 26, 10, 1024, 1)]
+if len(sys.argv) > 1:
+    plans = [p for p in plans if p[0] in sys.argv[1:]]
+for name, n, rounds, block, per_sm in plans:
     tmc.set_option("philox_rounds", rounds)
     tmc.set_option("block_threads", block)
+    tmc.set_option("blocks_per_sm", per_sm)
     tmc.photons_fx(name, 1, 0, n >> 3)
     best = None
     for rep in range(3):
