@@ -68,10 +68,10 @@ void orc_fx_plan(const orc_optics* o, orc_fx_scales* s)
 {
     const float albedo = o->mu_s / (o->mu_s + o->mu_a);
     const double absorb = 1.0 - (double)albedo;
-    /* weight 1.0 -> 2^heat_shift, chosen so that the largest deposit is in [2^20, 2^21). */
-    int hs = 21 - (int)ceil(log2(absorb));
+    /* weight 1.0 -> 2^heat_shift, chosen so that the largest deposit is in [2^17, 2^18). */
+    int hs = 18 - (int)ceil(log2(absorb));
     if (hs > 30) hs = 30;
-    if (hs < 16) hs = 16;
+    if (hs < 14) hs = 14;
     s->heat_shift = (uint32_t)hs;
     s->weight_one = 1u << hs;
     double q = floor(absorb * 4294967296.0 + 0.5);
@@ -80,7 +80,7 @@ void orc_fx_plan(const orc_optics* o, orc_fx_scales* s)
     s->absorb_q32 = (uint32_t)q;
     const uint64_t dep_max = ((uint64_t)s->weight_one * s->absorb_q32) >> 32;
     const uint32_t bits = ceil_log2_u64(dep_max + 1);
-    s->heat2_rshift = (2 * bits > 22) ? 2 * bits - 22 : 0;
+    s->heat2_rshift = (2 * bits > 18) ? 2 * bits - 18 : 0;
     s->roulette_thr = (uint32_t)floor(0.001 * (double)s->weight_one + 0.5);
 }
 

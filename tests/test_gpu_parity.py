@@ -202,6 +202,40 @@ def test_config2_full_size_properties(gpu):
     assert np.array_equal(a[0], heat_fx) and np.array_equal(a[1], heat2_fx)
 
 
+def test_config4_full_size_properties(gpu):
+    """BASELINE configs[3]: high albedo (MU_A=0.1, MU_S=100), 2^30 photons = 7.7e12 events:
+    size-independent properties of the walk (reference photon.c:32,45-49)."""
+    n = 1 << 30
+    heat_fx, heat2_fx = gpu.photons_fx("highalbedo", SEED, 0, n)
+    info = gpu.last_run_info()
+    heat, heat2 = gpu.capi.fx_to_float64("highalbedo", heat_fx, heat2_fx)
+    a = albedo(gpu.CONFIGS["highalbedo"])
+    assert info.photons == n and info.retries == 0
+    assert abs(heat.sum() / n - 1.0) < 2e-6                                      # E[absorbed] = 1 (roulette unbiased)
+    assert abs(heat2.sum() / n / ((1 - a) / (1 + a)) - 1.0) < 1e-3
+    assert abs(info.events / n - 7168.0) < 4.0                                   # 6912 + 2304 / 9 (deterministic schedule)
+    ref = np.load(GOLDEN / "port_xoshiro_batches_highalbedo.npz")
+    extra_ref = ref["heat"][:, -1].sum() / (ref["heat"].shape[0] * int(ref["photons_per_batch"]))
+    assert abs(heat[-1] / n - extra_ref) < 2e-3                                  # overflow-bin share ~0.235
+
+
+def test_config5_full_size_properties(gpu):
+    """BASELINE configs[4]: SHELLS=16384, 5 um shells, 2^30 photons (one shared histogram per block)."""
+    n = 1 << 30
+    heat_fx, heat2_fx = gpu.photons_fx("finegrid", SEED, 0, n)
+    info = gpu.last_run_info()
+    heat, heat2 = gpu.capi.fx_to_float64("finegrid", heat_fx, heat2_fx)
+    assert info.photons == n and info.retries == 0
+    assert abs(heat.sum() / n - 1.0) < 2e-6
+    assert abs(heat2.sum() / n * 21.0 - 1.0) < 1e-3
+    assert abs(info.events / n - 75.665) < 0.01
+    assert heat[-1] / n < 1e-6                                                   # 8.2 cm grid: the overflow bin stays empty
+    # the fine grid is the default grid refined 10x: regrouped it is the same profile as config 2
+    coarse, _ = gpu.capi.fx_to_float64("default", *gpu.photons_fx("default", SEED + 1, 0, 1 << 26))
+    mine = heat[:1000].reshape(100, 10).sum(axis=1) / n
+    assert np.abs(mine / (coarse[:100] / (1 << 26)) - 1.0).max() < 5e-3
+
+
 # ------------------------------------------------------------------ the reference-facing calls
 def test_photons_adds_into_caller_arrays_like_photon_does(gpu):
     """tmc_photons() is `for (...) photon(heat, heat2)`: it only ADDS (reference photon.c:30-31)."""
@@ -246,7 +280,15 @@ def test_device_resident_call_on_a_torch_stream(gpu):
 def test_headless_program_prints_the_reference_layout(gpu):
     """The C host program (tiny_mc_b200/host/tiny_mc.c) against the reference's own stdout."""
     exe = ROOT / "tiny_mc_b200" / "bin" / "headless"
-    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True, env={**os.environ, "TMC_GPUS": "1"}).stdout.splitlines()
+    js = ROOT / "gpurun_out" / "headless_test.json"
+    js.parent.mkdir(exist_ok=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True,
+                         env={**os.environ, "TMC_GPUS": "1", "TMC_JSON": str(js)}).stdout.splitlines()
+    import json
+    doc = json.loads(js.read_text())
+    assert doc["photons"] == 32768 and doc["shells"] == 101 and len(doc["heat"]) == 101
+    assert abs(sum(doc["heat"]) / doc["photons"] - 1.0) < 5 * 0.00301 / np.sqrt(32768)
+    assert sum(doc["heat_fx"]) == round(sum(doc["heat"]) * 2 ** doc["heat_shift"])
     gold = (GOLDEN / "headless_asshipped.txt").read_text().splitlines()
     assert len(out) == len(gold)
     assert out[:2] == gold[:2] and out[3:7] == gold[3:7] and out[9:11] == gold[9:11]

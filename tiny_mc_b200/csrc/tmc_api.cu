@@ -119,9 +119,9 @@ int make_plan(const tmc_params* p, Plan* pl)
     pl->shells_per_mfp = static_cast<float>(1e4 / static_cast<double>(p->microns_per_shell) /
                                             static_cast<double>(p->mu_a + p->mu_s));
     const double absorb = 1.0 - static_cast<double>(pl->albedo);
-    int hs = 21 - static_cast<int>(std::ceil(std::log2(absorb)));
+    int hs = 18 - static_cast<int>(std::ceil(std::log2(absorb)));   // largest deposit in [2^17, 2^18)
     if (hs > 30) hs = 30;
-    if (hs < 16) hs = 16;
+    if (hs < 14) hs = 14;
     pl->sc.heat_shift = static_cast<uint32_t>(hs);
     pl->weight_one = 1u << hs;
     double q = std::floor(absorb * 4294967296.0 + 0.5);
@@ -130,7 +130,7 @@ int make_plan(const tmc_params* p, Plan* pl)
     pl->sc.absorb_q32 = static_cast<uint32_t>(q);
     const uint64_t dep_max = (static_cast<uint64_t>(pl->weight_one) * pl->sc.absorb_q32) >> 32;
     const uint32_t bits = ceil_log2_u64(dep_max + 1);
-    pl->sc.heat2_rshift = (2 * bits > 22) ? 2 * bits - 22 : 0;
+    pl->sc.heat2_rshift = (2 * bits > 18) ? 2 * bits - 18 : 0;
     pl->heat2_half = pl->sc.heat2_rshift ? (1u << (pl->sc.heat2_rshift - 1)) : 0u;
     pl->sc.roulette_thr = static_cast<uint32_t>(std::floor(0.001 * pl->weight_one + 0.5));
     // Generation g = number of roulettes survived.  Every photon of a generation starts it with
@@ -349,7 +349,7 @@ double shells_per_mfp_of(const tmc_params* p)
     return 1e4 / static_cast<double>(p->microns_per_shell) / static_cast<double>(p->mu_a + p->mu_s);
 }
 
-int configure_launch(const tmc_params* p, int device_sms, uint64_t count, uint32_t flush_override, LaunchCfg* cfg)
+int configure_launch(const tmc_params* p, const Plan& pl, int device_sms, uint64_t count, uint32_t flush_override, LaunchCfg* cfg)
 {
     bool lane_private = p->shells <= tmc::kLanePrivateMaxShells;
     if (g.opt.tally_layout == 1) lane_private = false;
@@ -381,17 +381,32 @@ int configure_launch(const tmc_params* p, int device_sms, uint64_t count, uint32
     if (flush == 0) {
         // Philox blocks (3 events for each of a warp's 64 photons) between two drains of the u32
         // block histograms; deposits are < 2^21.
+        // the largest amount one event adds to a heat or to a heat2 word
+        const uint64_t dep0 = (static_cast<uint64_t>(pl.weight_one) * pl.sc.absorb_q32 + 0x80000000ull) >> 32;
+        const uint64_t dep20 = (dep0 * dep0 + pl.heat2_half) >> pl.sc.heat2_rshift;
+        const double d0 = static_cast<double>(dep0 > dep20 ? dep0 : dep20);
         if (lane_private) {
-            // A (shell, lane) slot only ever sees the 2 photons per warp of its own lane: even if
-            // all of them sat in one shell at full weight, 2^32 / (2 * warps * 3 * 2^21) blocks
-            // cannot wrap the word; the 2^31 check then catches anything above half of that.
-            flush = static_cast<uint32_t>(2048u / (6u * warps));
+            // A (shell, lane) slot only ever sees the 2 photons per warp of its own lane.  Two hard
+            // bounds on what they can add to one u32 word between two drains.  A slice is drained
+            // once per `warps` drain calls; in between a warp walks at most 2 * flush blocks (its own
+            // calls may fall anywhere in the interval), i.e. 6 * flush events per photon slot:
+            //  (a) every event deposits at most the first deposit d0: 12 * warps * flush * d0 < 2^32;
+            //  (b) a photon deposits at most its whole weight 2^heat_shift in its life, and at most
+            //      ceil(6 * flush / K0) + 1 lives per photon slot touch the interval.
+            // Either suffices, so the larger interval is taken; the 2^31 check stays as a tripwire.
+            const double by_event = 4294967296.0 / (12.0 * static_cast<double>(warps) * (d0 + 1.0));
+            const double lives = 4294967296.0 / (2.0 * static_cast<double>(warps) * static_cast<double>(pl.weight_one)) - 1.0;
+            const double by_life = lives >= 2.0 ? (std::floor(lives) - 1.0) * static_cast<double>(pl.gen[0].n_events) / 6.0 : 0.0;
+            double blocks = by_event > by_life ? by_event : by_life;
+            if (blocks > 512.0) blocks = 512.0;
+            flush = blocks < 1.0 ? 1u : static_cast<uint32_t>(blocks);
         } else {
-            // One histogram per block: bound the busiest shell by the first-collision share
-            // 1 - exp(-1/shells_per_mfp) <= 1/shells_per_mfp of a block's photons (x2 margin).
+            // One histogram per block: the busiest shell takes at most the first-collision share
+            // 1 - exp(-1/shells_per_mfp) <= 1/shells_per_mfp of a block's events (x2 margin here, and
+            // the target is 2^31, half of what would wrap; the 2^31 check catches the rest).
             double share = 2.0 / static_cast<double>(shells_per_mfp_of(p));
             if (share > 1.0) share = 1.0;
-            const double blocks = 2147483648.0 / (64.0 * static_cast<double>(warps) * 3.0 * share * 2097152.0);
+            const double blocks = 2147483648.0 / (64.0 * static_cast<double>(warps) * 6.0 * share * (d0 + 1.0));
             flush = blocks > 64.0 ? 64u : (blocks < 1.0 ? 1u : static_cast<uint32_t>(blocks));
         }
         if (flush < 1u) flush = 1u;
@@ -432,7 +447,7 @@ int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t fi
         uint64_t n = count < (1ull << 30) ? count : (1ull << 30);
         if (n > window_left) n = window_left;
         LaunchCfg cfg{};
-        rc = configure_launch(p, device_sms, n, flush_override, &cfg);
+        rc = configure_launch(p, pl, device_sms, n, flush_override, &cfg);
         if (rc) return rc;
         if (!have_first && first_cfg) *first_cfg = cfg;
         have_first = true;

@@ -4,7 +4,10 @@
  * (reference tiny_mc.c:34-69); the per-photon loop `for (i < PHOTONS) photon(heat, heat2)`
  * (reference tiny_mc.c:47-49) becomes ONE call of tmc_photons().  Host code stays plain C11.
  *
- * Environment: TMC_GPUS=<n> selects how many GPUs to use (default: all visible).
+ * Environment: TMC_GPUS=<n> selects how many GPUs to use (default: all visible);
+ * TMC_JSON=<path> additionally writes the exact tallies in machine-readable form (SURVEY §8f
+ * rank 1: the float printout of the reference loses digits at large PHOTONS; the reference's
+ * own stdout contract is untouched).
  */
 #include "params.h"
 #include "report.h"
@@ -12,12 +15,42 @@
 #include "wtime.h"
 
 #include <assert.h>
+#include <inttypes.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 
 /* caller-owned tallies, zero-initialised by static storage like reference tiny_mc.c:26-27 */
 static float heat[SHELLS];
 static float heat2[SHELLS];
+/* the same tallies as exact fixed-point integers (bit-identical for any GPU count) */
+static uint64_t heat_fx[SHELLS];
+static uint64_t heat2_fx[SHELLS];
+
+static void write_json(const char* path, const tmc_params* params, uint64_t seed, uint64_t photons, double seconds)
+{
+    tmc_scales sc;
+    tmc_run_info info;
+    FILE* f = fopen(path, "w");
+    if (!f || tmc_fx_scales(params, &sc) != TMC_OK || tmc_last_run_info(&info) != TMC_OK) {
+        fprintf(stderr, "tiny_mc_b200: cannot write %s\n", path);
+        if (f) fclose(f);
+        return;
+    }
+    const double s1 = ldexp(1.0, -(int)sc.heat_shift), s2 = ldexp(1.0, (int)sc.heat2_rshift - 2 * (int)sc.heat_shift);
+    fprintf(f, "{\"shells\": %u, \"mu_a\": %.9g, \"mu_s\": %.9g, \"microns_per_shell\": %.9g, \"photons\": %" PRIu64
+               ", \"seed\": %" PRIu64 ", \"seconds\": %.9g, \"events\": %" PRIu64 ", \"n_gpus\": %u, \"kernel_ms\": %.6f,\n",
+            params->shells, params->mu_a, params->mu_s, params->microns_per_shell, photons, seed, seconds, info.events,
+            info.n_gpus, info.kernel_ms);
+    fprintf(f, " \"heat_shift\": %u, \"heat2_rshift\": %u,\n \"heat\": [", sc.heat_shift, sc.heat2_rshift);
+    for (unsigned i = 0; i < SHELLS; ++i) fprintf(f, "%s%.17g", i ? ", " : "", (double)heat_fx[i] * s1);
+    fprintf(f, "],\n \"heat2\": [");
+    for (unsigned i = 0; i < SHELLS; ++i) fprintf(f, "%s%.17g", i ? ", " : "", (double)heat2_fx[i] * s2);
+    fprintf(f, "],\n \"heat_fx\": [");
+    for (unsigned i = 0; i < SHELLS; ++i) fprintf(f, "%s%" PRIu64, i ? ", " : "", heat_fx[i]);
+    fprintf(f, "]}\n");
+    fclose(f);
+}
 
 int main(void)
 {
@@ -35,7 +68,8 @@ int main(void)
 
     const uint64_t seed = (uint64_t)(SEED); /* role of srand(SEED), reference tiny_mc.c:43 */
     const double start = wtime();
-    const int rc = tmc_photons(&params, seed, 0, photons, heat, heat2);
+    int rc = tmc_photons_fx(&params, seed, 0, photons, heat_fx, heat2_fx);
+    if (rc == TMC_OK) rc = tmc_fx_accumulate(&params, heat_fx, heat2_fx, heat, heat2);   /* the += of photon.c:30-31 */
     const double end = wtime();
     if (rc != TMC_OK) {
         fprintf(stderr, "tiny_mc_b200: %s\n", tmc_last_error());
@@ -45,6 +79,7 @@ int main(void)
 
     tmc_report_timing(stdout, end - start, photons);
     tmc_report_table(stdout, SHELLS, (float)(MICRONS_PER_SHELL), photons, heat, heat2);
+    if (getenv("TMC_JSON")) write_json(getenv("TMC_JSON"), &params, seed, photons, end - start);
     tmc_finalize();
     return 0;
 }
