@@ -22,6 +22,12 @@ ncu)
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu launches rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:photon_walk -s 1 -c 1 -f -o gpurun_out/prof \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?" ;;
+ncucfg)
+  for c in highalbedo finegrid; do
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:photon_walk -s 1 -c 1 -f -o gpurun_out/prof_$c \
+        python bench.py --config $c --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_$c.log 2>&1; echo "ncu $c rc=$?"
+    timeout 600 python bench.py --config $c --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; echo "bench $c rc=$?"
+  done ;;
 microncu)
   timeout 900 ncu --metrics sm__cycles_elapsed.avg,smsp__inst_executed.sum,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,sm__issue_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum \
       --clock-control none --csv --log-file gpurun_out/micro_ncu.csv tiny_mc_b200/bin/tmc_microbench > gpurun_out/micro_under_ncu.jsonl 2>&1; echo "microncu rc=$?" ;;
