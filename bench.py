@@ -35,6 +35,7 @@ import tempfile
 import time
 from pathlib import Path
 
+_JSON_FD = None
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
@@ -155,7 +156,16 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -357,13 +367,19 @@ def run_ours(args):
         per_core = args.cpu_photons_per_core or ((1 << 18) if args.config != "highalbedo" else (1 << 11))
         _, cpu = cpu_reference_run(args.config, per_core)
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: NCCL and torchrun print banners ("NCCL version ...") on fd 1,
+    # so everything else is sent to stderr and the line is written to the saved descriptor.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
