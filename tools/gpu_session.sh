@@ -28,6 +28,8 @@ ncucfg)
         python bench.py --config $c --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_$c.log 2>&1; echo "ncu $c rc=$?"
     timeout 600 python bench.py --config $c --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; echo "bench $c rc=$?"
   done ;;
+sanitize)
+  for t in memcheck racecheck initcheck; do timeout 900 compute-sanitizer --tool $t --error-exitcode 9 python tools/sanitize_run.py > gpurun_out/sanitizer_$t.log 2>&1; echo "sanitizer $t rc=$?"; tail -2 gpurun_out/sanitizer_$t.log; done ;;
 microncu)
   timeout 900 ncu --metrics sm__cycles_elapsed.avg,smsp__inst_executed.sum,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,sm__issue_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum \
       --clock-control none --csv --log-file gpurun_out/micro_ncu.csv tiny_mc_b200/bin/tmc_microbench > gpurun_out/micro_under_ncu.jsonl 2>&1; echo "microncu rc=$?" ;;
