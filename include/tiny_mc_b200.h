@@ -74,6 +74,11 @@ typedef struct tmc_run_info {
  * Creates streams and tally buffers; with n_gpus > 1 also one NCCL communicator per device
  * (single process, ncclCommInitAll).  One-off cost, excluded from every timing.            */
 int tmc_init(int n_gpus);
+/* Optional, after tmc_init: pay the remaining one-off costs for `p` now (device buffers, the
+ * azimuth and deposit tables, kernel attributes, the first NCCL collective) by walking 64
+ * photons per device into a scratch tally, so that the first timed tmc_photons* call measures
+ * the walk.  The reference has no counterpart (its photon() has no set-up).                   */
+int tmc_prepare(const tmc_params* p);
 int tmc_finalize(void);
 int tmc_device_count(void);            /* devices in use after tmc_init, else 0 */
 const char* tmc_last_error(void);

@@ -21,5 +21,6 @@ from .capi import (  # noqa: F401
     photons,
     photons_device,
     photons_fx,
+    prepare,
     set_option,
 )

