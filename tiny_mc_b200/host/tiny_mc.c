@@ -27,6 +27,40 @@ static float heat2[SHELLS];
 static uint64_t heat_fx[SHELLS];
 static uint64_t heat2_fx[SHELLS];
 
+/* batch-means standard error of the per-photon mean heat of every shell (filled when TMC_JSON is set):
+ * the estimator the reference's Error column (tiny_mc.c:64) is not - that one sums squares per EVENT and is
+ * NaN-prone.  Splitting the range changes nothing else: the sum of the batches is bit-identical. */
+#define TMC_BATCHES 16
+static double heat_stderr[SHELLS];
+static int have_stderr = 0;
+
+static int walk_in_batches(const tmc_params* params, uint64_t seed, uint64_t photons)
+{
+    static uint64_t b_heat[SHELLS], b_heat2[SHELLS];
+    static double sum[SHELLS], sum_sq[SHELLS];
+    uint64_t done = 0;
+    for (int b = 0; b < TMC_BATCHES; ++b) {
+        const uint64_t n = photons / TMC_BATCHES + ((uint64_t)b < photons % TMC_BATCHES ? 1 : 0);
+        for (unsigned i = 0; i < SHELLS; ++i) b_heat[i] = b_heat2[i] = 0;
+        const int rc = tmc_photons_fx(params, seed, done, n, b_heat, b_heat2);
+        if (rc != TMC_OK) return rc;
+        for (unsigned i = 0; i < SHELLS; ++i) {
+            const double m = n ? (double)b_heat[i] / (double)n : 0.0;
+            heat_fx[i] += b_heat[i];
+            heat2_fx[i] += b_heat2[i];
+            sum[i] += m;
+            sum_sq[i] += m * m;
+        }
+        done += n;
+    }
+    for (unsigned i = 0; i < SHELLS; ++i) {
+        const double mean = sum[i] / TMC_BATCHES, var = (sum_sq[i] / TMC_BATCHES - mean * mean) * TMC_BATCHES / (TMC_BATCHES - 1.0);
+        heat_stderr[i] = sqrt((var > 0.0 ? var : 0.0) / TMC_BATCHES);
+    }
+    have_stderr = 1;
+    return TMC_OK;
+}
+
 static void write_json(const char* path, const tmc_params* params, uint64_t seed, uint64_t photons, double seconds)
 {
     tmc_scales sc;
@@ -46,6 +80,10 @@ static void write_json(const char* path, const tmc_params* params, uint64_t seed
     for (unsigned i = 0; i < SHELLS; ++i) fprintf(f, "%s%.17g", i ? ", " : "", (double)heat_fx[i] * s1);
     fprintf(f, "],\n \"heat2\": [");
     for (unsigned i = 0; i < SHELLS; ++i) fprintf(f, "%s%.17g", i ? ", " : "", (double)heat2_fx[i] * s2);
+    if (have_stderr) {
+        fprintf(f, "],\n \"heat_per_photon_stderr_fx_units\": [");
+        for (unsigned i = 0; i < SHELLS; ++i) fprintf(f, "%s%.9g", i ? ", " : "", heat_stderr[i]);
+    }
     fprintf(f, "],\n \"heat_fx\": [");
     for (unsigned i = 0; i < SHELLS; ++i) fprintf(f, "%s%" PRIu64, i ? ", " : "", heat_fx[i]);
     fprintf(f, "]}\n");
@@ -73,7 +111,8 @@ int main(void)
 
     const uint64_t seed = (uint64_t)(SEED); /* role of srand(SEED), reference tiny_mc.c:43 */
     const double start = wtime();
-    int rc = tmc_photons_fx(&params, seed, 0, photons, heat_fx, heat2_fx);
+    int rc = (getenv("TMC_JSON") && photons >= 64u * TMC_BATCHES) ? walk_in_batches(&params, seed, photons)
+                                                                     : tmc_photons_fx(&params, seed, 0, photons, heat_fx, heat2_fx);
     if (rc == TMC_OK) rc = tmc_fx_accumulate(&params, heat_fx, heat2_fx, heat, heat2);   /* the += of photon.c:30-31 */
     const double end = wtime();
     if (rc != TMC_OK) {
