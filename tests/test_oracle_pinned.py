@@ -132,7 +132,7 @@ def test_libc_rand_biases_the_reference_itself():
 
 
 def test_replay_agrees_with_reference_walk_on_sound_rng(orc):
-    """tmc-stream-1 (Philox, direct direction sampling, fixed-point weights) vs the reference walk
+    """tmc-stream-3 (Philox, direct direction sampling, fixed-point weights) vs the reference walk
     (photon_port.c: rejection sampling, float weights) on xoshiro256**: every shell within 4 sigma."""
     from stats import batch_means_z
 
