@@ -88,7 +88,8 @@ int tmc_abi_version(void);
 /* Tunables: "philox_rounds" (10 = default, or 7), "block_threads" (128..1024), "blocks_per_sm"
  * (1..4: residency, and with it the register budget of the kernel variant),
  * "flush_iters", "nccl_reduce" (1 = NCCL, 0 = host-side sum; default 1), "tally_layout"
- * (0 = auto, 1 = one histogram per block, 2 = one per lane).  0 restores the default.           */
+ * (0 = auto, 1 = one histogram per block, 2 = one per lane), "tally_check_bits" (31; tests lower
+ * it to exercise the TMC_ERR_TALLY_RANGE retry).  0 restores the default.                      */
 int tmc_set_option(const char* name, long long value);
 
 /* The batched form of the reference call site tiny_mc.c:47-49:

@@ -280,6 +280,28 @@ def test_bad_arguments_on_a_gpu(gpu):
     assert b"shared memory" in lib.tmc_last_error()
 
 
+def test_tally_range_tripwire_retries_then_fails_loudly(gpu):
+    """A drained u32 word at or above 2^tally_check_bits makes the host repeat the range with an 8x
+    shorter drain interval; if that never helps the call fails with TMC_ERR_TALLY_RANGE instead of
+    returning tallies that may have wrapped."""
+    base = gpu.photons_fx("default", SEED, 0, 1 << 20)
+    outcomes = {}
+    for bits in range(26, 11, -2):
+        gpu.set_option("tally_check_bits", bits)
+        try:
+            again = gpu.photons_fx("default", SEED, 0, 1 << 20)
+            outcomes[bits] = gpu.last_run_info().retries
+            assert np.array_equal(again[0], base[0]) and np.array_equal(again[1], base[1]), bits
+        except gpu.TinyMcError as e:
+            assert e.code == 5
+            outcomes[bits] = -e.code
+        finally:
+            gpu.set_option("tally_check_bits", 0)
+    assert outcomes[26] == 0                         # far above what 2^20 photons can pile up
+    assert any(v >= 1 for v in outcomes.values()), outcomes      # some threshold is rescued by shorter intervals
+    assert outcomes[12] == -5, outcomes              # below a single deposit: fails loudly with TMC_ERR_TALLY_RANGE
+
+
 def test_device_resident_call_on_a_torch_stream(gpu):
     import torch
 

@@ -63,6 +63,7 @@ struct Options {
     int flush_iters = 0;     // 0 = auto
     int nccl_reduce = 1;
     int tally_layout = 0;    // 0 = auto, 1 = plain per-block histogram, 2 = lane-private
+    int tally_check_bits = 31;   // a drained u32 word >= 2^bits triggers the retry (tests lower it)
 };
 
 struct Lib {
@@ -456,6 +457,7 @@ int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t fi
         a.first = first;
         a.count = n;
         a.flush_blocks = cfg.flush_iters;
+        a.check_shift = static_cast<uint32_t>(g.opt.tally_check_bits);
         void* params[] = { &a };
         CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(cfg.fn), dim3(cfg.grid), dim3(cfg.block), params, cfg.smem, stream));
         g.info.gpu_launches += 1;
@@ -725,6 +727,10 @@ int tmc_set_option(const char* name, long long value)
         g.opt.flush_iters = static_cast<int>(value);
     } else if (n == "nccl_reduce") {
         g.opt.nccl_reduce = value ? 1 : 0;
+    } else if (n == "tally_check_bits") {
+        if (value == 0) value = 31;
+        if (value < 8 || value > 31) return fail(TMC_ERR_BAD_ARG, "tally_check_bits must be 8..31");
+        g.opt.tally_check_bits = static_cast<int>(value);
     } else if (n == "tally_layout") {
         if (value < 0 || value > 2) return fail(TMC_ERR_BAD_ARG, "tally_layout must be 0 (auto), 1 (plain) or 2 (lane-private)");
         g.opt.tally_layout = static_cast<int>(value);

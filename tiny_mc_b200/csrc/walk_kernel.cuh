@@ -70,6 +70,7 @@ struct WalkArgs {
     uint32_t shells;                // SHELLS (reference params.h:5)
     uint32_t last_bits;             // 0x4B000000 + SHELLS-1 : clamp in the magic-number domain
     uint32_t flush_blocks;          // Philox blocks (3 events) a warp walks between drains
+    uint32_t check_shift;           // a drained word >= 2^check_shift raises the range flag (31)
     uint32_t n_gen;                 // generations in `gen` (a photon surviving them all is dropped)
     GenPlan gen[kMaxGenerations];
 };
@@ -146,7 +147,8 @@ struct IntTag {
 // atomicExch: no barrier needed, the other warps keep adding meanwhile.  Called by a whole
 // converged warp; returns bit 0 set when a word had come within a factor two of wrapping.
 template <int BLOCK, bool LANE_PRIVATE>
-__device__ __noinline__ uint32_t drain_slice(uint32_t* bins, unsigned long long* tallies, uint32_t shells, uint32_t slice)
+__device__ __noinline__ uint32_t drain_slice(uint32_t* bins, unsigned long long* tallies, uint32_t shells, uint32_t slice,
+                                             uint32_t check_shift)
 {
     constexpr uint32_t WARPS = BLOCK / 32;
     const uint32_t lane = threadIdx.x & 31u;
@@ -155,7 +157,7 @@ __device__ __noinline__ uint32_t drain_slice(uint32_t* bins, unsigned long long*
         const uint32_t rows = 2u * shells;             // row = shell * 2 + kind, 32 lanes wide
         for (uint32_t row = slice; row < rows; row += WARPS) {
             const uint32_t v = atomicExch(&bins[row * 32u + lane], 0u);
-            flag |= v >> 31;
+            flag |= v >> check_shift;
             if (__any_sync(0xffffffffu, v != 0u)) {
                 const uint32_t lo = __reduce_add_sync(0xffffffffu, v & 0xFFFFu);
                 const uint32_t hi = __reduce_add_sync(0xffffffffu, v >> 16);
@@ -168,7 +170,7 @@ __device__ __noinline__ uint32_t drain_slice(uint32_t* bins, unsigned long long*
         for (uint32_t i = slice * 32u + lane; i < 2u * plain_bins; i += BLOCK) {
             const uint32_t v = atomicExch(&bins[i], 0u);
             if (v != 0u) {
-                flag |= v >> 31;
+                flag |= v >> check_shift;
                 const uint32_t kind = i >= plain_bins ? 1u : 0u;
                 const uint32_t s = min(i - kind * plain_bins, shells - 1u);
                 atomicAdd(&tallies[kind * shells + s], static_cast<unsigned long long>(v));
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
         uint32_t ticket = 0u;
         if (lane == 0u) ticket = atomicAdd(&drain_ticket, 1u);
         range_flag |= drain_slice<BLOCK, LANE_PRIVATE>(smem + kAzimuthBytes / 4u, a.tallies, a.shells,
-                                                       __shfl_sync(0xffffffffu, ticket, 0) % WARPS);
+                                                       __shfl_sync(0xffffffffu, ticket, 0) % WARPS, a.check_shift);
     };
 
     // One scatter event (reference photon.c:21-43) of slot S of the current Philox block for
@@ -487,13 +489,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
 
     // Final drain once every warp of the block is done.
     __syncthreads();
-    range_flag |= drain_slice<BLOCK, LANE_PRIVATE>(smem + kAzimuthBytes / 4u, a.tallies, a.shells, wid);
+    range_flag |= drain_slice<BLOCK, LANE_PRIVATE>(smem + kAzimuthBytes / 4u, a.tallies, a.shells, wid, a.check_shift);
     uint32_t fl = range_flag;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);
     if (lane == 0u) {
         atomicAdd(&a.counters[0], n_events);
-        if (fl) atomicOr(&a.counters[2], 1ull);
+        if (fl != 0u) atomicOr(&a.counters[2], 1ull);
     }
     if (tid == 0u && blockIdx.x == 0u) atomicAdd(&a.counters[1], static_cast<unsigned long long>(a.count));
 }
