@@ -193,7 +193,7 @@ def run_ours(args):
     shells = cfg["shells"]
     per_gpu = args.photons_per_gpu or ((1 << 26) if world == 1 else (1 << 29))
     if args.config == "highalbedo" and not args.photons_per_gpu:
-        per_gpu >>= 6
+        per_gpu >>= 4    # 2^22 photons = 3e10 events per step: ~28 cohorts per warp, so the one-cohort tail is ~1 %
     per_step = per_gpu * world
     seed = 0x5EED
     tmc.set_option("philox_rounds", args.philox_rounds)

@@ -10,8 +10,8 @@ import tiny_mc_b200 as tmc  # noqa: E402
 tmc.init(1)
 plans = [("default", 1 << 26, 10, 0, 0), ("default", 1 << 26, 7, 0, 0), ("default", 1 << 26, 10, 256, 2), ("default", 1 << 26, 10, 256, 3),
          ("default", 1 << 26, 10, 256, 4), ("default", 1 << 26, 10, 512, 1), ("default", 1 << 26, 10, 512, 2), ("default", 1 << 26, 10, 1024, 1),
-         ("default", 1 << 26, 10, 128, 4), ("highalbedo", 1 << 20, 10, 0, 0), ("highalbedo", 1 << 20, 10, 1024, 1), ("finegrid", 1 << 26, 10, 0, 0),
-         ("finegrid", 1 << 26, 10, 1024, 1)]
+         ("default", 1 << 26, 10, 128, 4), ("highalbedo", 1 << 20, 10, 0, 0), ("highalbedo", 1 << 20, 10, 1024, 1), ("highalbedo", 1 << 20, 10, 256, 2),
+         ("highalbedo", 1 << 20, 10, 256, 3), ("highalbedo", 1 << 20, 10, 128, 4), ("finegrid", 1 << 26, 10, 0, 0), ("finegrid", 1 << 26, 10, 512, 1)]
 if len(sys.argv) > 1:
     plans = [p for p in plans if p[0] in sys.argv[1:]]
 for name, n, rounds, block, per_sm in plans:
