@@ -121,6 +121,14 @@ int tmc_photons_device(const tmc_params* p, uint64_t seed, uint64_t first_photon
 /* Fixed-point scales used for `p` (a pure function of the optics). */
 int tmc_fx_scales(const tmc_params* p, tmc_scales* out);
 
+/* The deterministic weight schedule behind the kernel: generation g (= number
+ * of roulettes survived, reference photon.c:45-48) starts at scatter event first_event[g]
+ * (1-based), lasts n_events[g] events and starts with fixed-point weight w_start[g].
+ * Fills up to max_gen entries, returns the number filled (or a negative status).  Pure host
+ * arithmetic: works without a GPU.                                                           */
+int tmc_generation_plan(const tmc_params* p, uint32_t max_gen, uint32_t* first_event, uint32_t* n_events,
+                        uint32_t* w_start);
+
 /* Convert / accumulate fixed-point tallies into the reference's float arrays (+=). */
 int tmc_fx_accumulate(const tmc_params* p, const uint64_t* heat_fx, const uint64_t* heat2_fx,
                       float* heats, float* heats_squared);

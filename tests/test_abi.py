@@ -21,7 +21,7 @@ def declared_symbols():
 def test_library_exports_every_declared_symbol(tmc):
     lib = tmc.load()
     names = declared_symbols()
-    assert len(names) >= 14 and set(names) == set(tmc.capi.EXPORTS)
+    assert len(names) >= 15 and set(names) == set(tmc.capi.EXPORTS)
     for name in names:
         assert getattr(lib, name) is not None
     dyn = subprocess.run(["nm", "-D", "--defined-only", str(tmc.lib_path())], capture_output=True, text=True, check=True).stdout
@@ -100,3 +100,26 @@ def test_fx_accumulate_adds_like_photon_does(tmc):
     tmc.fx_accumulate("default", heat_fx, heat2_fx, heats, heats2)
     assert np.allclose(heats, 1.5 + np.arange(101) / 8.0)
     assert np.allclose(heats2, 0.25 + 3 * np.arange(101) * 2.0 ** (sc.heat2_rshift - 2 * sc.heat_shift), rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["default", "highalbedo", "finegrid"])
+def test_weight_schedule_matches_oracle_and_the_reference_walk(tmc, orc, name):
+    """The deterministic weight schedule the kernel is built on: product and
+    oracle derive it independently, and it is what the reference's float arithmetic does
+    (reference photon.c:32,45-48: w *= albedo until w < 0.001, then x10 on survival)."""
+    mine = tmc.generation_plan(name, 8)
+    theirs = orc.generation_plan(name, 8)
+    for a, b in zip(mine, theirs):
+        assert np.array_equal(a, b)
+    first, n, w = mine
+    assert first[0] == 1 and np.array_equal(first[1:], first[:-1] + n[:-1])
+    cfg = tmc.CONFIGS[name]
+    albedo = np.float32(cfg["mu_s"]) / (np.float32(cfg["mu_s"]) + np.float32(cfg["mu_a"]))
+    wf, k = np.float32(1.0), 0                      # generation 0 in the reference's own float arithmetic
+    while True:
+        wf = np.float32(wf * albedo)
+        k += 1
+        if wf < np.float32(0.001):
+            break
+    assert n[0] == k                                # 73 (default, fine grid), 6912 (high albedo): SURVEY §4
+    assert abs(float(w[1]) / float(w[0]) - 10.0 * float(wf)) < 2e-5

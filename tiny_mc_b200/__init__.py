@@ -13,6 +13,7 @@ from .capi import (  # noqa: F401
     TinyMcError,
     fx_accumulate,
     fx_scales,
+    generation_plan,
     init,
     finalize,
     last_run_info,

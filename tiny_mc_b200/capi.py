@@ -76,7 +76,7 @@ CONFIGS = {
 EXPORTS = (
     "tmc_init", "tmc_prepare", "tmc_finalize", "tmc_device_count", "tmc_last_error", "tmc_version",
     "tmc_abi_version", "tmc_set_option", "tmc_photons", "tmc_photons_fx", "tmc_photons_device",
-    "tmc_fx_scales", "tmc_fx_accumulate", "tmc_last_run_info",
+    "tmc_fx_scales", "tmc_fx_accumulate", "tmc_generation_plan", "tmc_last_run_info",
 )
 
 _lib = None
@@ -107,6 +107,7 @@ def load() -> C.CDLL:
     lib.tmc_fx_scales.argtypes = [C.POINTER(Params), C.POINTER(Scales)]
     lib.tmc_fx_accumulate.argtypes = [C.POINTER(Params), p, p, p, p]
     lib.tmc_last_run_info.argtypes = [C.POINTER(RunInfo)]
+    lib.tmc_generation_plan.argtypes = [C.POINTER(Params), C.c_uint32, p, p, p]
     _lib = lib
     return lib
 
@@ -182,6 +183,16 @@ def fx_scales(cfg) -> Scales:
 def fx_accumulate(cfg, heat_fx: np.ndarray, heat2_fx: np.ndarray, heats: np.ndarray, heats_squared: np.ndarray):
     p = make_params(cfg)
     _check(load().tmc_fx_accumulate(C.byref(p), heat_fx.ctypes.data, heat2_fx.ctypes.data, heats.ctypes.data, heats_squared.ctypes.data))
+
+
+def generation_plan(cfg, max_gen: int = 8):
+    """(first_event, n_events, w_start) per generation of the deterministic weight schedule."""
+    prm = make_params(cfg)
+    a, b, c = (np.zeros(max_gen, np.uint32) for _ in range(3))
+    n = load().tmc_generation_plan(C.byref(prm), max_gen, a.ctypes.data, b.ctypes.data, c.ctypes.data)
+    if n < 0:
+        _check(-n)
+    return a[:n], b[:n], c[:n]
 
 
 def fx_to_float64(cfg, heat_fx: np.ndarray, heat2_fx: np.ndarray):

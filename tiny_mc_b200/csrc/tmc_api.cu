@@ -750,6 +750,21 @@ int tmc_fx_scales(const tmc_params* p, tmc_scales* out)
     return TMC_OK;
 }
 
+int tmc_generation_plan(const tmc_params* p, uint32_t max_gen, uint32_t* first_event, uint32_t* n_events, uint32_t* w_start)
+{
+    if (!first_event || !n_events || !w_start) return -fail(TMC_ERR_BAD_ARG, "NULL pointer");
+    Plan pl;
+    const int rc = make_plan(p, &pl);
+    if (rc) return -rc;
+    const uint32_t n = max_gen < pl.n_gen ? max_gen : pl.n_gen;
+    for (uint32_t g = 0; g < n; ++g) {
+        first_event[g] = pl.gen[g].first_event;
+        n_events[g] = pl.gen[g].n_events;
+        w_start[g] = pl.gen[g].w_start;
+    }
+    return static_cast<int>(n);
+}
+
 int tmc_fx_accumulate(const tmc_params* p, const uint64_t* heat_fx, const uint64_t* heat2_fx, float* heats, float* heats_squared)
 {
     if (!heat_fx || !heat2_fx || !heats || !heats_squared) return fail(TMC_ERR_BAD_ARG, "NULL pointer");
