@@ -322,7 +322,7 @@ def run_ours(args):
         "bound": "issue",
         "achieved": achieved / 1e12, "peak": issue_peak / 1e12, "unit": "T lane-instr/s",
         "frac": achieved / issue_peak,
-        "traffic": 21760,
+        "traffic": 79104,   # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu capture profiles/r01_v5_default_ncu.md
         "definition": "events/s/GPU x 88 canonical issue slots per event (SURVEY 8d: walk 35 + Philox4x32-10 53) "
                       "/ (SMs x 128 lanes/clk x SM clock sampled during the run)",
         "frac_walk_only_35_slots": events_per_s_per_gpu * WALK_SLOTS_PER_EVENT / issue_peak,
@@ -336,7 +336,7 @@ def run_ours(args):
                           "shared-pipe utilisation; frac > 1 means fewer instructions than the canonical 88-slot budget",
         "philox10_ceiling_events_per_s": sms * 4 * f_sm_hz / 80.0 * 32 * 3,
         "frac_of_philox10_ceiling": events_per_s_per_gpu / (sms * 4 * f_sm_hz / 80.0 * 32 * 3),
-        "bytes_note": "HBM traffic is ~20 KB per launch (ncu dram__bytes): the kernel reads no input",
+        "bytes_note": "HBM traffic is ~80 KB per launch (ncu dram__bytes): the kernel reads no input",
     }
 
     line = {
