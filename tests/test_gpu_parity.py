@@ -90,6 +90,37 @@ def test_single_photon_and_empty_range(gpu, orc):
     assert not h.any() and not h2.any() and gpu.last_run_info().photons == 0
 
 
+@pytest.mark.parametrize("cfg,n", [
+    (dict(shells=101, mu_a=5.0, mu_s=0.0, microns_per_shell=50.0), 20000),        # pure absorber: one event per generation
+    (dict(shells=1, mu_a=2.0, mu_s=20.0, microns_per_shell=50.0), 5000),          # a single (overflow) bin
+    (dict(shells=37, mu_a=1.0, mu_s=3.0, microns_per_shell=400.0), 20000),        # low albedo, coarse shells: generations of 5 events
+    (dict(shells=512, mu_a=0.5, mu_s=60.0, microns_per_shell=20.0), 4000),        # largest lane-private grid
+    (dict(shells=513, mu_a=0.5, mu_s=60.0, microns_per_shell=20.0), 4000),        # smallest shared-histogram grid
+    (dict(shells=2000, mu_a=3.0, mu_s=9.0, microns_per_shell=500.0), 20000),      # coarse shells in the shared histogram: hot bins
+])
+def test_other_optics_equal_the_replay(gpu, orc, cfg, n):
+    """Run-time parameters (reference params.h:5-23 are compile-time): whatever the optics, events
+    and fixed-point totals equal the CPU replay exactly, per-shell words up to MUFU shell flips."""
+    heat_fx, heat2_fx = gpu.photons_fx(cfg, 31337, 5, n)
+    info = gpu.last_run_info()
+    r_heat, r_heat2, r_events = orc.replay(cfg, 31337, 5, n)
+    assert info.events == r_events and info.retries == 0
+    assert int(heat_fx.sum()) == int(r_heat.sum()) and int(heat2_fx.sum()) == int(r_heat2.sum())
+    moved = np.abs(heat_fx.astype(np.int64) - r_heat.astype(np.int64)).sum() / 2
+    assert moved <= 2e-3 * r_heat.sum()
+    if cfg["mu_s"] == 0.0:
+        # every photon deposits its whole weight at the first collision: heat[s] / N is the exponential
+        # step distribution integrated over the shell (reference photon.c:21,26)
+        heat, _ = gpu.capi.fx_to_float64(cfg, heat_fx, heat2_fx)
+        spm = 1e4 / cfg["microns_per_shell"] / (cfg["mu_a"] + cfg["mu_s"])
+        edges = np.arange(cfg["shells"]) / spm
+        expect = np.exp(-edges) - np.exp(-(edges + 1.0 / spm))
+        expect[-1] = np.exp(-edges[-1])
+        sigma = np.sqrt(expect * (1 - expect) / n)
+        assert np.abs(heat / n - expect).max() < 5 * sigma.max() + 1e-4
+        assert abs(heat.sum() / n - 1.0) < 1e-6
+
+
 # ------------------------------------------------------------------ 2. bit-reproducibility
 @pytest.mark.parametrize("name,n", [("default", 300000), ("highalbedo", 3000), ("finegrid", 200000)])
 def test_result_is_independent_of_split_and_launch_shape(gpu, name, n):

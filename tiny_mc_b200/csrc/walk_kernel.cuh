@@ -356,9 +356,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) r[j][k] = cur[j][k];
-            if (b == 0u) {                       // pseudo-event 0: the fate word
-                fate[0] = r[0][0];
-                fate[1] = r[1][0];
+            if (g == 0u && b == 0u) {            // pseudo-event 0 of a fresh photon: its fate word
+                fate[0] = r[0][0];               // (short generations can start inside block 0 too:
+                fate[1] = r[1][0];               //  those carry their fate, already multiplied by 10)
             }
             if (s_lo == 0u) { absorb(); event(IntTag<0>{}, partial_tag, dep, dep2); }
             if (s_lo <= 1u && s_hi >= 1u) { absorb(); event(IntTag<1>{}, partial_tag, dep, dep2); }
