@@ -651,6 +651,24 @@ int tmc_finalize(void)
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     g.devs.clear();
+    // cached tables and scratch (recreated lazily by the next call on that device)
+    for (int d = 0; d < 64; ++d)
+        if (g_azimuth[d]) {
+            cudaSetDevice(d);
+            cudaDeviceSynchronize();
+            cudaFree(const_cast<float2*>(g_azimuth[d]));
+            g_azimuth[d] = nullptr;
+        }
+    for (DepositTable& t : g_deposit_tables) {
+        cudaSetDevice(t.device);
+        cudaFree(t.d_table);
+    }
+    g_deposit_tables.clear();
+    for (QueueScratch& q : g_queue_scratch) {
+        cudaSetDevice(q.device);
+        cudaFree(q.d_buf);
+    }
+    g_queue_scratch.clear();
     if (g.h_pinned) cudaFreeHost(g.h_pinned);
     g.h_pinned = nullptr;
     g.h_words = 0;
