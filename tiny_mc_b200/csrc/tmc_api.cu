@@ -339,7 +339,13 @@ int kernel_occupancy(KernelFn fn, int block, size_t smem, int* per_sm)
             *per_sm = k.per_sm;
             return TMC_OK;
         }
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // allow the largest block this device offers once and for all: the attribute is per function, and
+    // setting it to each request's size would LOWER it again for a later, larger request
+    int optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cudaFuncAttributes fattr;
+    CUDA_TRY(cudaFuncGetAttributes(&fattr, fn));
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - static_cast<int>(fattr.sharedSizeBytes)));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, block, smem));
     g_kernel_facts.push_back(KernelFacts{ fn, dev, block, smem, *per_sm });
     return TMC_OK;
