@@ -58,10 +58,11 @@ def main():
 
     # chunk = photons per fresh float tally.  High albedo makes ~7150 deposits of
     # ~1e-3 * w per photon: even 256-photon float chunks lose 1.3e-4 of the weight, so 8 there.
-    # n = photons per batch of the libc-rand() reference, n_good = of the xoshiro port (4x more:
+    # n = photons per batch of the libc-rand() reference, n_good = of the xoshiro port (32x / 16x more:
+    # 1.3e8 photons resolve ~0.05 % per shell, the level at which the product's 42-bit events could show;
     # a 4.2e6-photon sample once sat 3.5 sigma low over shells 60-76 and failed a correct kernel).
-    plans = (("default", 64, 1 << 16, 1 << 18, 256), ("highalbedo", 64, 1 << 10, 1 << 12, 8),
-             ("finegrid", 64, 1 << 16, 1 << 18, 256))
+    plans = (("default", 64, 1 << 16, 1 << 21, 256), ("highalbedo", 64, 1 << 10, 1 << 14, 8),
+             ("finegrid", 64, 1 << 16, 1 << 21, 256))
     only = set(sys.argv[1:])
     for name, nb, n, n_good, chunk in plans:
         if only and name not in only:

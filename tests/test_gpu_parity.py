@@ -186,11 +186,12 @@ def group(a, name):
     return a.reshape(a.shape[0], 128, 128).sum(axis=2) if name == "finegrid" else a
 
 
-@pytest.mark.parametrize("name,nb,n", [("default", 64, 1 << 20), ("highalbedo", 64, 1 << 13), ("finegrid", 64, 1 << 20)])
+@pytest.mark.parametrize("name,nb,n", [("default", 64, 1 << 22), ("highalbedo", 64, 1 << 15), ("finegrid", 64, 1 << 22)])
 def test_every_shell_within_4_sigma_of_the_reference_walk(gpu, name, nb, n):
     """The north-star tolerance: per-shell mean heat within 4 sigma, total absorbed weight to
     1e-4 relative.  Reference side: photon_port.c (bit-identical to reference photon.c) on
-    xoshiro256**, 64 batches; sigma: batch means on both sides."""
+    xoshiro256**, 64 batches of 2^21 photons (2^14 for high albedo): 1.3e8 reference photons against
+    2.7e8 GPU photons resolve ~0.05 % per shell; sigma: batch means on both sides."""
     ref = np.load(GOLDEN / f"port_xoshiro_batches_{name}.npz")
     n_ref = int(ref["photons_per_batch"])
     heat, heat2 = gpu_batches(gpu, name, nb, n)

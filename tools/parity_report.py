@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""tools/parity_report.py — the numbers behind tests/test_gpu_parity.py::test_every_shell_within_4_sigma...:
+per configuration max |z|, mean z, shells beyond 3 sigma, total absorbed weight of both sides (run on a B200)."""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import tiny_mc_b200 as tmc  # noqa: E402
+from stats import batch_means_z, literal_sigma_z  # noqa: E402
+
+tmc.init(1)
+out = {}
+for name, nb, n in (("default", 64, 1 << 22), ("highalbedo", 64, 1 << 15), ("finegrid", 64, 1 << 22)):
+    ref = np.load(ROOT / "tests" / "golden" / f"port_xoshiro_batches_{name}.npz")
+    n_ref = int(ref["photons_per_batch"])
+    heat, heat2 = [], []
+    for b in range(nb):
+        h, h2 = tmc.capi.fx_to_float64(name, *tmc.photons_fx(name, 0x5EED, b * n, n))
+        heat.append(h)
+        heat2.append(h2)
+    heat, heat2 = np.stack(heat), np.stack(heat2)
+    g = heat.reshape(nb, 128, 128).sum(axis=2) if name == "finegrid" else heat
+    z, ok = batch_means_z(g, n, ref["heat"], n_ref, min_mean=1e-4)
+    rel_sigma = np.sqrt((g / n).var(axis=0, ddof=1) / nb + (ref["heat"] / n_ref).var(axis=0, ddof=1) / ref["heat"].shape[0])[ok] / (g / n).mean(axis=0)[ok]
+    zl = literal_sigma_z(heat.sum(0), heat2.sum(0), nb * n, ref["heat"].sum(0) if name != "finegrid" else heat.sum(0), ref["heat2"].sum(0) if name != "finegrid" else heat2.sum(0), 64 * n_ref if name != "finegrid" else nb * n)
+    out[name] = dict(gpu_photons=nb * n, reference_photons=64 * n_ref, shells_tested=int(ok.sum()), max_abs_z=float(np.abs(z[ok]).max()),
+                     mean_z=float(z[ok].mean()), shells_beyond_3_sigma=int((np.abs(z[ok]) > 3).sum()),
+                     median_relative_sigma_per_shell=float(np.median(rel_sigma)),
+                     absorbed_per_photon_gpu=float(heat.sum() / (nb * n)), absorbed_per_photon_reference=float(ref["heat"].sum() / (64 * n_ref)),
+                     literal_heat2_sigma_max_abs_z=(None if name == "finegrid" else float(np.nanmax(np.abs(zl[:-1])))),
+                     literal_heat2_sigma_nan_shells=(None if name == "finegrid" else int(np.isnan(zl).sum())),
+                     z=[round(float(v), 2) for v in z[ok]])
+tmc.finalize()
+print(json.dumps(out, indent=1))
