@@ -29,7 +29,19 @@ $(BINDIR)/tmc_microbench: $(CSRC)/microbench.cu
 	@mkdir -p $(BINDIR)
 	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<
 
-host: $(BINDIR)/headless $(LIBDIR)/libphoton_compat.so
+host: $(BINDIR)/headless $(LIBDIR)/libphoton_compat.so configs
+
+# the named configurations of BASELINE.json as host programs (compile-time macros, like the reference)
+CONFIG2 = -DPHOTONS=67108864ULL -DSEED=24301
+CONFIG3 = -DPHOTONS=4294967296ULL -DSEED=24301
+CONFIG4 = -DPHOTONS=1073741824ULL -DSEED=24301 -DMU_A=0.1f -DMU_S=100.0f
+CONFIG5 = -DPHOTONS=1073741824ULL -DSEED=24301 -DSHELLS=16384 -DMICRONS_PER_SHELL=5
+configs: $(BINDIR)/headless_config2 $(BINDIR)/headless_config3 $(BINDIR)/headless_config4 $(BINDIR)/headless_config5
+
+$(BINDIR)/headless_config%: $(HOST)/tiny_mc.c $(HOST)/report.c $(HOST)/wtime.c $(LIB)
+	@mkdir -p $(BINDIR)
+	$(CC) $(CFLAGS) $(CONFIG$*) -Iinclude -I$(HOST) -o $@ $(HOST)/tiny_mc.c $(HOST)/report.c $(HOST)/wtime.c \
+	    -L$(LIBDIR) -ltinymc_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
 
 $(BINDIR)/headless: $(HOST)/tiny_mc.c $(HOST)/report.c $(HOST)/wtime.c $(LIB)
 	@mkdir -p $(BINDIR)
@@ -48,4 +60,4 @@ clean:
 	rm -rf $(LIBDIR) $(BINDIR)
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib host oracle clean
+.PHONY: all lib host configs oracle clean

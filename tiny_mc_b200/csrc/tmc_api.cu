@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -485,6 +486,9 @@ int check_device_arch(int dev)
 int load_nccl()
 {
     if (g.nccl.handle) return TMC_OK;
+    // NCCL prints its banner ("NCCL version ...", NCCL_DEBUG=VERSION/INFO) on stdout by default; stdout
+    // belongs to the host program's printout (reference tiny_mc.c:37-66), so send it to stderr.
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     const char* names[] = { "libnccl.so.2", "libnccl.so" };
     for (const char* n : names) {
         g.nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
