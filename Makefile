@@ -29,7 +29,7 @@ $(BINDIR)/tmc_microbench: $(CSRC)/microbench.cu
 	@mkdir -p $(BINDIR)
 	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<
 
-host: $(BINDIR)/headless $(LIBDIR)/libphoton_compat.so configs
+host: $(BINDIR)/headless $(BINDIR)/frames $(LIBDIR)/libphoton_compat.so configs
 
 # the named configurations of BASELINE.json as host programs (compile-time macros, like the reference)
 CONFIG2 = -DPHOTONS=67108864ULL -DSEED=24301
@@ -47,6 +47,11 @@ $(BINDIR)/headless: $(HOST)/tiny_mc.c $(HOST)/report.c $(HOST)/wtime.c $(LIB)
 	@mkdir -p $(BINDIR)
 	$(CC) $(CFLAGS) $(DEFS) -Iinclude -I$(HOST) -o $@ $(HOST)/tiny_mc.c $(HOST)/report.c $(HOST)/wtime.c \
 	    -L$(LIBDIR) -ltinymc_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lm
+
+# the viewer's incremental use of the tallies (reference cg_mc.c:71-87) without the OpenGL part
+$(BINDIR)/frames: $(HOST)/frames.c $(LIB)
+	@mkdir -p $(BINDIR)
+	$(CC) $(CFLAGS) -DSEED=4242 $(DEFS) -Iinclude -I$(HOST) -o $@ $(HOST)/frames.c -L$(LIBDIR) -ltinymc_b200 -Wl,-rpath,'$$ORIGIN/../lib'
 
 $(LIBDIR)/libphoton_compat.so: $(HOST)/photon_compat.c $(LIB)
 	$(CC) $(CFLAGS) $(DEFS) -Iinclude -I$(HOST) -fPIC -shared -o $@ $(HOST)/photon_compat.c \

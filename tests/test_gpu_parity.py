@@ -375,6 +375,22 @@ def test_headless_program_prints_the_reference_layout(gpu):
     assert out[-1].startswith("# extra\t") and abs(float(out[-1].split("\t")[1]) - 0.0235) < 3e-3
 
 
+def test_frames_program_accumulates_like_the_viewer(gpu):
+    """Incremental use of the tallies (reference cg_mc.c:71-87): 16 frames of 4096 photons into the
+    same running arrays give exactly the one-shot result."""
+    exe = ROOT / "tiny_mc_b200" / "bin" / "frames"
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    frames = [line for line in out if line.startswith("frame")]
+    assert len(frames) == 16 and frames[-1].split("\t")[1] == "photons 65536"
+    gpu.init(1)
+    hfx, h2fx = gpu.photons_fx("default", 4242, 0, 65536)
+    checksum = 0
+    for a, b in zip(hfx.tolist(), h2fx.tolist()):
+        checksum = (checksum * 1000003 + a + 31 * b) % (1 << 64)
+    assert out[-1] == f"# checksum\t{checksum}"
+    assert abs(float(frames[-1].split("absorbed/photon ")[1]) - 1.0) < 5 * 0.00301 / np.sqrt(65536)
+
+
 def test_photon_compat_shim_is_one_photon_per_call(gpu):
     """`void photon(float*, float*)` (reference photon.h:3): k calls == photons [0, k)."""
     lib = C.CDLL(str(ROOT / "tiny_mc_b200" / "lib" / "libphoton_compat.so"))
