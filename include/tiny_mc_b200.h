@@ -89,7 +89,10 @@ int tmc_abi_version(void);
  * (1..4: residency, and with it the register budget of the kernel variant),
  * "flush_iters", "nccl_reduce" (1 = NCCL, 0 = host-side sum; default 1), "tally_layout"
  * (0 = auto, 1 = one histogram per block, 2 = one per lane), "tally_check_bits" (31; tests lower
- * it to exercise the TMC_ERR_TALLY_RANGE retry).  0 restores the default.                      */
+ * it to exercise the TMC_ERR_TALLY_RANGE retry), "walk_mode" (0 = the 3-D walk of reference
+ * photon.c:20-50; 1 = a reduced radial walk, r'^2 = r^2 + t^2 + 2 r t mu, distribution-identical for
+ * this isotropic problem: a cross-check, never the benchmarked path; default block shape only).
+ * 0 restores the default.                                                                     */
 int tmc_set_option(const char* name, long long value);
 
 /* The batched form of the reference call site tiny_mc.c:47-49:

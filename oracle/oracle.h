@@ -77,6 +77,9 @@ uint32_t orc_generation_plan(const orc_optics* o, uint32_t max_gen, uint32_t* fi
  * Returns number of scatter events. */
 uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n,
                     uint64_t* heat_fx, uint64_t* heat2_fx);
+/* mode 0 = the 3-D walk (orc_replay), 1 = the product's reduced radial cross-check walk. */
+uint64_t orc_replay_mode(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n, int mode,
+                         uint64_t* heat_fx, uint64_t* heat2_fx);
 
 #ifdef __cplusplus
 }

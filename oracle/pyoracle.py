@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         l.orc_fx_plan.argtypes = [C.POINTER(Optics), C.POINTER(FxScales)]
         l.orc_replay.restype = C.c_uint64
         l.orc_replay.argtypes = [C.POINTER(Optics), C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        l.orc_replay_mode.restype = C.c_uint64
+        l.orc_replay_mode.argtypes = [C.POINTER(Optics), C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         l.orc_generation_plan.restype = C.c_uint32
         l.orc_generation_plan.argtypes = [C.POINTER(Optics), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = l
@@ -146,12 +148,13 @@ def fx_plan(cfg) -> FxScales:
     return s
 
 
-def replay(cfg, seed: int, first: int, n: int, rounds: int = 10):
-    """CPU replay of the product's Philox stream: exact u64 fixed-point tallies + event count."""
+def replay(cfg, seed: int, first: int, n: int, rounds: int = 10, mode: int = 0):
+    """CPU replay of the product's Philox stream: exact u64 fixed-point tallies + event count.
+    mode 0 = the 3-D walk, 1 = the reduced radial cross-check walk."""
     o = optics(cfg)
     heat = np.zeros(o.shells, np.uint64)
     heat2 = np.zeros(o.shells, np.uint64)
-    ev = lib().orc_replay(C.byref(o), rounds, seed, first, n, heat.ctypes.data, heat2.ctypes.data)
+    ev = lib().orc_replay_mode(C.byref(o), rounds, seed, first, n, mode, heat.ctypes.data, heat2.ctypes.data)
     return heat, heat2, int(ev)
 
 

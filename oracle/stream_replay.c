@@ -115,6 +115,15 @@ uint32_t orc_generation_plan(const orc_optics* o, uint32_t max_gen, uint32_t* fi
 uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n,
                     uint64_t* heat_fx, uint64_t* heat2_fx)
 {
+    return orc_replay_mode(o, rounds, seed, first, n, 0, heat_fx, heat2_fx);
+}
+
+/* mode 0: the 3-D walk; mode 1: the product's reduced radial cross-check walk ("walk_mode" = 1):
+ * r'^2 = r^2 + t^2 + (t r)(2 mu), mu = cos between r and the new direction, uniform on [-1, 1]
+ * because scattering is isotropic (photon.c:35-43) — same step, same mu bits, no azimuth. */
+uint64_t orc_replay_mode(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n, int mode,
+                         uint64_t* heat_fx, uint64_t* heat2_fx)
+{
     orc_fx_scales s;
     orc_fx_plan(o, &s);
     const float spm = (float)(1e4 / (double)o->microns_per_shell / (double)(o->mu_a + o->mu_s));
@@ -158,19 +167,26 @@ uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_
             /* spin (photon.c:35-43, sampled directly, BEFORE the hop so that no direction is
              * carried between events): cos(theta) = (2k+1)/512 - 1 from bits 1..9, azimuth
              * from a 1024-entry table indexed by 10 bits of word 3 */
-            const float ct = fmaf((float)(8388608u + ((v & 0x3FEu) | 1u)), 0.001953125f, -16385.0f);
-            const float st = sqrtf(fmaf(-ct, ct, 1.0f));
-
             /* hop (photon.c:21-24): xi = 2 * (1.5 - f), f = 1 + (v >> 10) * 2^-23 */
             bits32 fb;
             fb.u = 0x3F800000u | (v >> 10);
             const float t = fmaf(log2f(1.5f - fb.f), -LN2, -LN2);
-            const float ts = t * st;
-            x = fmaf(t, ct, x);
-            y = fmaf(ts, az_cos[az], y);
-            z = fmaf(ts, az_sin[az], z);
-            /* drop (photon.c:26-32) */
-            const float rad = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+            float rad;
+            if (mode == 1) { /* reduced radial walk: x holds the radius, 2 mu = (2k+1)/256 - 2 */
+                const float mu2 = fmaf((float)(8388608u + ((v & 0x3FEu) | 1u)), 0.00390625f, -32770.0f);
+                const float r2 = fmaf(t * x, mu2, fmaf(t, t, x * x));
+                rad = sqrtf(r2 > 0.0f ? r2 : 0.0f);
+                x = rad;
+            } else {
+                const float ct = fmaf((float)(8388608u + ((v & 0x3FEu) | 1u)), 0.001953125f, -16385.0f);
+                const float st = sqrtf(fmaf(-ct, ct, 1.0f));
+                const float ts = t * st;
+                x = fmaf(t, ct, x);
+                y = fmaf(ts, az_cos[az], y);
+                z = fmaf(ts, az_sin[az], z);
+                /* drop (photon.c:26-32) */
+                rad = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+            }
             const double sf = floor((double)rad * (double)spm);
             const uint32_t shell = (sf >= (double)last) ? last : (uint32_t)sf;
             const uint32_t dep = (uint32_t)(((uint64_t)w * s.absorb_q32 + 0x80000000ull) >> 32);

@@ -121,6 +121,33 @@ def test_other_optics_equal_the_replay(gpu, orc, cfg, n):
         assert abs(heat.sum() / n - 1.0) < 1e-6
 
 
+def test_radial_cross_check_mode(gpu, orc):
+    """"walk_mode" = 1: the reduced radial walk equals its own CPU replay in every
+    integer, and agrees statistically with the 3-D walk (the product) at 2^28 photons per side."""
+    gpu.set_option("walk_mode", 1)
+    try:
+        for name, n in (("default", 20000), ("finegrid", 20000)):
+            h, h2 = gpu.photons_fx(name, SEED, 77, n)
+            ev = gpu.last_run_info().events
+            r, r2, rev = orc.replay(name, SEED, 77, n, mode=1)
+            assert ev == rev and int(h.sum()) == int(r.sum()) and int(h2.sum()) == int(r2.sum())
+            assert np.abs(h.astype(np.int64) - r.astype(np.int64)).sum() / 2 <= 6e-3 * r.sum()
+        radial = gpu_batches(gpu, "default", 32, 1 << 23, seed=99)
+    finally:
+        gpu.set_option("walk_mode", 0)
+    full = gpu_batches(gpu, "default", 32, 1 << 23, seed=99)
+    z, ok = batch_means_z(radial[0], 1 << 23, full[0], 1 << 23)
+    assert ok.all() and np.abs(z).max() < 4.5 and abs(z.mean()) < 0.6, z
+    gpu.set_option("walk_mode", 1)
+    gpu.set_option("block_threads", 256)
+    try:
+        with pytest.raises(gpu.TinyMcError):          # compiled for the default launch shape only
+            gpu.photons_fx("default", SEED, 0, 1000)
+    finally:
+        gpu.set_option("block_threads", 0)
+        gpu.set_option("walk_mode", 0)
+
+
 # ------------------------------------------------------------------ 2. bit-reproducibility
 @pytest.mark.parametrize("name,n", [("default", 300000), ("highalbedo", 3000), ("finegrid", 200000)])
 def test_result_is_independent_of_split_and_launch_shape(gpu, name, n):

@@ -65,6 +65,7 @@ struct Options {
     int nccl_reduce = 1;
     int tally_layout = 0;    // 0 = auto, 1 = plain per-block histogram, 2 = lane-private
     int tally_check_bits = 31;   // a drained u32 word >= 2^bits triggers the retry (tests lower it)
+    int walk_mode = 0;           // 0 = the 3-D walk (the product), 1 = the reduced radial walk (cross-check only)
 };
 
 struct Lib {
@@ -215,8 +216,18 @@ KernelFn kernel_for_block(int block, int per_sm)
     }
 }
 
-KernelFn pick_kernel(int rounds, int block, int per_sm, bool lane_private)
+// the reduced radial walk ("walk_mode" = 1) is compiled for the default shapes only
+template <int ROUNDS>
+KernelFn radial_kernel(int block, int per_sm, bool lane_private)
 {
+    if (lane_private && block == 512 && per_sm == 1) return tmc::photon_walk_kernel<ROUNDS, 512, 1, true, true>;
+    if (!lane_private && block == 1024 && per_sm == 1) return tmc::photon_walk_kernel<ROUNDS, 1024, 1, false, true>;
+    return nullptr;
+}
+
+KernelFn pick_kernel(int rounds, int block, int per_sm, bool lane_private, bool radial)
+{
+    if (radial) return rounds == 10 ? radial_kernel<10>(block, per_sm, lane_private) : rounds == 7 ? radial_kernel<7>(block, per_sm, lane_private) : nullptr;
     switch (rounds) {
     case 7: return lane_private ? kernel_for_block<7, true>(block, per_sm) : kernel_for_block<7, false>(block, per_sm);
     case 10: return lane_private ? kernel_for_block<10, true>(block, per_sm) : kernel_for_block<10, false>(block, per_sm);
@@ -373,9 +384,11 @@ int configure_launch(const tmc_params* p, const Plan& pl, int device_sms, uint64
     const int smem_fit = static_cast<int>((227u * 1024u) / (smem + 1024u));
     if (want > smem_fit) want = smem_fit;
     KernelFn fn = nullptr;
-    for (int c = want; c >= 1 && !fn; --c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private);   // largest budget <= want
-    for (int c = want + 1; c <= 4 && !fn; ++c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private);   // else the next one
-    if (!fn) return fail(TMC_ERR_BAD_ARG, "no kernel for philox_rounds=%d block_threads=%d blocks_per_sm=%d", g.opt.philox_rounds, block, g.opt.blocks_per_sm);
+    for (int c = want; c >= 1 && !fn; --c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private, g.opt.walk_mode == 1);   // largest budget <= want
+    for (int c = want + 1; c <= 4 && !fn; ++c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private, g.opt.walk_mode == 1);   // else the next one
+    if (!fn)
+        return fail(TMC_ERR_BAD_ARG, "no kernel for philox_rounds=%d block_threads=%d blocks_per_sm=%d walk_mode=%d", g.opt.philox_rounds,
+                    block, g.opt.blocks_per_sm, g.opt.walk_mode);
     int per_sm = 0;
     int orc = kernel_occupancy(fn, block, smem, &per_sm);
     if (orc) return orc;
@@ -759,6 +772,9 @@ int tmc_set_option(const char* name, long long value)
         if (value == 0) value = 31;
         if (value < 8 || value > 31) return fail(TMC_ERR_BAD_ARG, "tally_check_bits must be 8..31");
         g.opt.tally_check_bits = static_cast<int>(value);
+    } else if (n == "walk_mode") {
+        if (value != 0 && value != 1) return fail(TMC_ERR_BAD_ARG, "walk_mode must be 0 (3-D walk) or 1 (radial cross-check)");
+        g.opt.walk_mode = static_cast<int>(value);
     } else if (n == "tally_layout") {
         if (value < 0 || value > 2) return fail(TMC_ERR_BAD_ARG, "tally_layout must be 0 (auto), 1 (plain) or 2 (lane-private)");
         g.opt.tally_layout = static_cast<int>(value);

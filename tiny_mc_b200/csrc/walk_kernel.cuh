@@ -183,7 +183,12 @@ __device__ __noinline__ uint32_t drain_slice(uint32_t* bins, unsigned long long*
 }
 
 // LANE_PRIVATE: bins[shell][kind][lane] (u32), kind 0 = heat, 1 = heat2; else heat[shells+31] | heat2[shells+31]
-template <int ROUNDS, int BLOCK, int MIN_BLOCKS, bool LANE_PRIVATE>
+// RADIAL: the reduced walk of SURVEY §8f rank 4 — only |r| is tallied and scattering is isotropic,
+//         so r'^2 = r^2 + t^2 + 2 r t mu with mu ~ U[-1, 1] is distribution-identical and needs neither
+//         a position vector nor an azimuth.  A separately selectable cross-check ("walk_mode" = 1):
+//         NOT the path the north star names (it skips the position update and the direction
+//         resampling), never used for the headline or the roofline figure.
+template <int ROUNDS, int BLOCK, int MIN_BLOCKS, bool LANE_PRIVATE, bool RADIAL = false>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __grid_constant__ WalkArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];     // [azimuth table 8 KB | histograms]
@@ -254,6 +259,22 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
         // The two photons of the lane are one packed FP32 pair wherever both need the same
         // operation (Blackwell FFMA2 / FMUL2 / FADD2: two results per issue slot); .x = photon 0.
         const uint32_t v0 = r[0][S], v1 = r[1][S];
+        float2 rad;
+        if constexpr (RADIAL) {
+            // mu = cos of the angle between r and the new direction, 2 mu = (2k+1)/256 - 2 from bits 1..9
+            const float2 mu2 = __ffma2_rn(make_float2(__uint_as_float((v0 & 0x3FEu) | 0x4B000001u), __uint_as_float((v1 & 0x3FEu) | 0x4B000001u)),
+                                          make_float2(0.00390625f, 0.00390625f), make_float2(-32770.0f, -32770.0f));
+            const float2 f = make_float2(__uint_as_float(__funnelshift_r(v0, 0xFEu, 10)), __uint_as_float(__funnelshift_r(v1, 0xFEu, 10)));
+            float2 lg = __fadd2_rn(make_float2(-f.x, -f.y), make_float2(1.5f, 1.5f));
+            lg.x = mufu_lg2(lg.x);
+            lg.y = mufu_lg2(lg.y);
+            const float2 t = __ffma2_rn(lg, make_float2(-kLn2, -kLn2), make_float2(-kLn2, -kLn2));
+            // px holds the radius of both photons: r'^2 = r^2 + t^2 + (t r)(2 mu), >= 0 up to rounding
+            const float2 r2 = __ffma2_rn(__fmul2_rn(t, px), mu2, __ffma2_rn(t, t, __fmul2_rn(px, px)));
+            rad.x = mufu_sqrt(fmaxf(r2.x, 0.0f));
+            rad.y = mufu_sqrt(fmaxf(r2.y, 0.0f));
+            px = rad;
+        } else {
         // spin: cos(theta) = (2k+1)/512 - 1 from bits 1..9 (exact), sin(theta) by MUFU.SQRT,
         // azimuth (cos, sin) from the table, indexed by 10 bits of word 3
         const float2 ct = __ffma2_rn(make_float2(__uint_as_float((v0 & 0x3FEu) | 0x4B000001u), __uint_as_float((v1 & 0x3FEu) | 0x4B000001u)),
@@ -285,9 +306,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
         // drop: shell = min(trunc(|r| * shells_per_mfp), SHELLS-1) without F2I: add 2^23 with
         // round-toward-zero, clamp the raw bits, the mantissa is the integer.
         const float2 xx = __fmul2_rn(px, px);
-        float2 rad;
         rad.x = mufu_sqrt(fmaf(pz[0], pz[0], fmaf(py[0], py[0], xx.x)));
         rad.y = mufu_sqrt(fmaf(pz[1], pz[1], fmaf(py[1], py[1], xx.y)));
+        }
         const float2 sbf = __ffma2_rz(rad, make_float2(a.shells_per_mfp, a.shells_per_mfp), make_float2(8388608.0f, 8388608.0f));
         const uint32_t sb[2] = { min(__float_as_uint(sbf.x), clamp_bits), min(__float_as_uint(sbf.y), clamp_bits) };
 #pragma unroll
