@@ -73,6 +73,10 @@ void orc_fx_plan(const orc_optics* o, orc_fx_scales* s);
 uint32_t orc_generation_plan(const orc_optics* o, uint32_t max_gen, uint32_t* first_event, uint32_t* n_events,
                              uint32_t* w_start);
 
+/* word -> step length [mfp] (bits 10..31) and word -> cos(theta) (bits 1..9) of the stream */
+float orc_step_of_word(uint32_t v);
+float orc_costheta_of_word(uint32_t v);
+
 /* Replay photons [first, first+n) of stream `seed`; ADD into u64 heat_fx/heat2_fx[shells].
  * Returns number of scatter events. */
 uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n,

@@ -112,6 +112,19 @@ uint32_t orc_generation_plan(const orc_optics* o, uint32_t max_gen, uint32_t* fi
     return g;
 }
 
+/* The two word -> variate mappings of the stream, exported for edge-case tests. */
+float orc_step_of_word(uint32_t v)
+{
+    bits32 fb;
+    fb.u = 0x3F800000u | (v >> 10);
+    return fmaf(log2f(1.5f - fb.f), -0.693147182464599609375f, -0.693147182464599609375f);
+}
+
+float orc_costheta_of_word(uint32_t v)
+{
+    return fmaf((float)(8388608u + ((v & 0x3FEu) | 1u)), 0.001953125f, -16385.0f);
+}
+
 uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n,
                     uint64_t* heat_fx, uint64_t* heat2_fx)
 {

@@ -173,3 +173,20 @@ def test_radial_replay_is_distribution_identical_to_the_3d_replay(orc):
     b = np.stack([orc.fx_to_float64("default", r[0], r[1])[0] for r in rad])
     z, ok = batch_means_z(a, n, b, n)
     assert ok.all() and np.abs(z).max() < 4.5 and abs(z.mean()) < 0.6
+
+
+def test_word_to_variate_mappings_have_no_singularities(orc):
+    """The reference's `-logf(rand() / RAND_MAX)` is +inf for rand() == 0 and NaN-poisons the photon
+    (photon.c:21-23); `sqrtf((1 - u*u) / t)` divides by zero for t == 0 (photon.c:42-43).
+    The stream's mappings are finite and well-centred for every input word."""
+    l = orc.lib()
+    assert l.orc_step_of_word(0x00000000) == 0.0                        # xi = 1
+    assert l.orc_step_of_word(0x000003FF) == 0.0                        # the low 10 bits are not step bits
+    longest = l.orc_step_of_word(0xFFFFFFFF)
+    assert abs(longest - 22 * np.log(2.0)) < 1e-5 and np.isfinite(longest)   # xi = 2^-22: 15.25 mean free paths
+    steps = np.array([l.orc_step_of_word(int(v)) for v in np.linspace(0, 2**32 - 1, 20001).astype(np.uint64)])
+    assert (np.diff(steps) >= 0).all() and abs(steps.mean() - 1.0) < 2e-3       # monotone, E[t] = 1
+    cos = np.array([l.orc_costheta_of_word(k << 1) for k in range(512)], np.float64)
+    assert np.array_equal(cos, (2 * np.arange(512) + 1) / 512.0 - 1.0)          # exact midpoints
+    assert cos.sum() == 0.0 and abs((cos**2).mean() * 3 - 1.0) < 4e-6 and np.abs(cos).max() < 1.0
+    assert l.orc_costheta_of_word(0xFFFFFC01) == cos[0]                          # only bits 1..9 matter
