@@ -104,7 +104,7 @@ uint32_t orc_generation_plan(const orc_optics* o, uint32_t max_gen, uint32_t* fi
         do {
             w -= (uint32_t)(((uint64_t)w * s.absorb_q32 + 0x80000000ull) >> 32);
             ++k;
-        } while (w >= s.roulette_thr && k < 0x40000000u);
+        } while (w >= s.roulette_thr && k < 0x400000u);
         n_events[g] = k;
         e += k;
         w *= 10u;

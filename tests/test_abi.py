@@ -67,6 +67,7 @@ def test_argument_validation(tmc):
     s = tmc.Scales()
     bad = [tmc.Params(0, 2.0, 20.0, 50.0), tmc.Params(101, 0.0, 20.0, 50.0), tmc.Params(101, 2.0, -1.0, 50.0),
            tmc.Params(101, 2.0, 20.0, 0.0)]
+    bad.append(tmc.Params(101, 1e-7, 100.0, 50.0))       # absorbed fraction 1e-9 per event: > 2^22 events per generation
     for p in bad:
         assert lib.tmc_fx_scales(C.byref(p), C.byref(s)) == 2
         assert lib.tmc_last_error()

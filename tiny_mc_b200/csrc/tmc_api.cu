@@ -148,9 +148,9 @@ int make_plan(const tmc_params* p, Plan* pl)
         do {
             w -= static_cast<uint32_t>((static_cast<uint64_t>(w) * pl->sc.absorb_q32 + 0x80000000ull) >> 32);
             ++k;
-        } while (w >= pl->sc.roulette_thr && k < (1u << 28));
-        if (w >= pl->sc.roulette_thr)
-            return fail(TMC_ERR_BAD_ARG, "MU_A / (MU_A + MU_S) = %g is too small: a photon needs > 2^28 events per generation", absorb);
+        } while (w >= pl->sc.roulette_thr && k < (1u << 22));
+        if (w >= pl->sc.roulette_thr)   // the deposit table would exceed ~300 MB (absorbed fraction per event below ~2e-6)
+            return fail(TMC_ERR_BAD_ARG, "MU_A / (MU_A + MU_S) = %g is too small: a photon needs > 2^22 events per generation", absorb);
         pl->gen[g].n_events = k;
         e += k;
         w *= 10u;
