@@ -156,6 +156,20 @@ BENCH_KERNEL(k_mix_2ffma_imadw, MIX_FI_DECL, REP8(MIX_2FI_), F_SINK ^ (unsigned)
 #define MIX_F2L_DECL FFMA2_DECL; U_DECL
 #define MIX_F2L_(i) FFMA2_(i) LOP3_(i)
 BENCH_KERNEL(k_mix_ffma2_lop3, MIX_F2L_DECL, REP4(MIX_F2L_) REP4(MIX_F2L_), (unsigned)(p0 ^ p1 ^ p2 ^ p3) ^ U_SINK)
+// Does IMAD.WIDE.U32 take one dispatch slot or two?  Philox-shaped true wide products (both halves live:
+// x = hi(x * M) ^ lo(x * M) ^ k), each group balanced over the three pipes: 4 FMA-heavy cycles (one
+// IMAD.WIDE, or two 32-bit IMADs in the reference kernel), 4 ALU cycles (2 LOP3), 4 FMA-lite cycles (2 FMUL).
+#define WIDE_DECL F_DECL; U_DECL
+#define WIDE_STEP_(i) asm volatile("{ .reg .u64 p; .reg .u32 lo, hi; mul.wide.u32 p, %0, 0xD2511F53; mov.b64 {lo, hi}, p; lop3.b32 %0, lo, hi, %1, 0x96; }" : "+r"(u##i) : "r"(kb));
+#define NARROW_STEP_(i) asm volatile("{ .reg .u32 a, b; mad.lo.u32 a, %0, 0xD2511F53, %1; mad.lo.u32 b, %0, 0xCD9E8D57, %1; lop3.b32 %0, a, b, %1, 0x96; }" : "+r"(u##i) : "r"(kb));
+#define EXTRA_LOP_(i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u##i) : "r"(ka), "r"(kb));
+#define WIDE_GROUP_(i) WIDE_STEP_(i) EXTRA_LOP_(i) FMUL_(i) FMUL_(i)
+#define NARROW_GROUP_(i) NARROW_STEP_(i) EXTRA_LOP_(i) FMUL_(i) FMUL_(i)
+BENCH_KERNEL(k_dispatch_imad_wide_group, WIDE_DECL, REP8(WIDE_GROUP_), F_SINK ^ U_SINK)
+BENCH_KERNEL(k_dispatch_two_imad_group, WIDE_DECL, REP8(NARROW_GROUP_), F_SINK ^ U_SINK)
+// the same with nothing but the wide products and their LOP3 (heavy-pipe bound: 4 cycles each)
+BENCH_KERNEL(k_imad_wide_live, U_DECL, REP8(WIDE_STEP_) REP8(WIDE_STEP_), U_SINK)
+
 // 7 FFMA : 1 MUFU
 #define MIX_FM_(i) FFMA_(i) FFMA_(i)
 BENCH_KERNEL(k_mix_14ffma_2mufu, F_DECL, REP8(MIX_FM_) LG2_(0) SQRT_(1), F_SINK)
@@ -325,6 +339,9 @@ int main(int argc, char** argv)
     SIMPLE(k_mix_fmul_imadw, 16);
     SIMPLE(k_mix_2ffma_imadw, 24);
     SIMPLE(k_mix_ffma2_lop3, 16);
+    SIMPLE(k_imad_wide_live, 32);              // 16 x (IMAD.WIDE + LOP3)
+    SIMPLE(k_dispatch_imad_wide_group, 40);    // 8 x (IMAD.WIDE + 2 LOP3 + 2 FMUL)
+    SIMPLE(k_dispatch_two_imad_group, 48);     // 8 x (2 IMAD + 2 LOP3 + 2 FMUL)
     SIMPLE(k_mix_14ffma_2mufu, 18);
     SIMPLE(k_mix_8ffma_8lop3_2mufu, 18);
     SIMPLE(k_philox10, 80);     // 2 x (20 IMAD.WIDE + 20 LOP3), key schedule folded by ptxas

@@ -23,7 +23,8 @@ print("# Pipe micro-benchmarks on the B200 (tiny_mc_b200/csrc/microbench.cu unde
 print("148 SMs x 4 sub-partitions; every kernel runs 32 warps per SM for 16384 iterations of 16-24 independent")
 print("instructions; rates are `smsp__inst_executed.sum / sm__cycles_elapsed.avg / 148` (loop overhead included),")
 print("pipe columns are ncu's own utilisation counters.  `k_imad_wide` was folded by ptxas into 32-bit IMADs")
-print("(its high half is dead) - the IMAD.WIDE.U32 rate is the one in `k_philox10` (20 IMAD.WIDE + 20 LOP3 per call).\n")
+print("(its high half is dead) - the IMAD.WIDE.U32 rate is the one in `k_imad_wide_live` (Philox-shaped: both halves of")
+print("every product are consumed) and `k_philox10` (20 IMAD.WIDE + 20 LOP3 per call).\n")
 print("| kernel | warp-inst / clk / SM | FMA-heavy busy % | FMA (heavy+lite) busy % | ALU % | XU % | issue % | shared wavefronts / clk / SM |")
 print("|---|---:|---:|---:|---:|---:|---:|---:|")
 for name, m in last.items():
@@ -39,8 +40,12 @@ Reading (these are the denominators DESIGN.md §7 uses):
 * scalar FP32 splits over FMA-heavy and FMA-lite; FFMA2 (packed f32x2), IMAD and LOP3/SHF/PRMT/I2FP run at
   2 warp-instructions / clk / SM (one 16-lane pipe each: FMA-heavy resp. ALU).  FFMA2 runs ONLY on FMA-heavy:
   same FP32 throughput as scalar code at half the issue slots.
-* IMAD.WIDE.U32 / IMAD.HI: ~4 heavy-pipe cycles per warp instruction (k_philox10: 0.26 IMAD.WIDE / clk / SMSP at
-  97 % heavy-pipe busy) - a Philox4x32-10 block costs ~80 heavy-pipe cycles per warp.
+* IMAD.WIDE.U32 / IMAD.HI: ~4 heavy-pipe cycles per warp instruction (k_imad_wide_live, k_philox10: 0.26 IMAD.WIDE /
+  clk / SMSP at 94-97 % heavy-pipe busy) - a Philox4x32-10 block costs ~80 heavy-pipe cycles per warp.
+* an IMAD.WIDE costs what TWO 32-bit IMADs cost: a pipe-balanced group {IMAD.WIDE, 2 LOP3, 2 FMUL} takes 7.25 cycles
+  per SMSP, the same group with {IMAD, IMAD} instead of the IMAD.WIDE 7.0 (k_dispatch_*); likewise FFMA2 + LOP3 pairs
+  reach 0.73 instructions / clk / SMSP with neither pipe saturated (k_mix_ffma2_lop3).  DESIGN.md §7 therefore counts
+  instructions with 64-bit register operands as two dispatch slots.
 * MUFU (lg2, sqrt, rsq, ex2, sin) and F2I: 0.5 warp-instructions / clk / SM = 16 lanes / clk / SM.
 * shared-memory atomics: ~1 wavefront / clk / SM; random 101-bin RED costs ~3.2 wavefronts per instruction,
   the lane-private layout exactly 1.
