@@ -28,3 +28,26 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_the_contract_keys():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "2", "--warmup", "3", "--no-cpu-baseline"],
+                         capture_output=True, text=True, check=True, timeout=600).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert key in d, key
+    assert d["metric"] == "photons/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["gpu_launches"] == 2 and d["vs_baseline"] is None
+    assert d["value"] > 1e9 and 0.5 < d["e2e"]["value"] / d["value"] < 1.1 and d["e2e"]["d2h_bytes_per_step"] == 8 * (2 * 101 + 4)
+    r = d["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in r, key
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.0 < r["frac_walk_only_35_slots"] < 1.0
+    assert "workload" in d["config"] and "BASELINE configs[1]" in d["config"]["workload"]
+    assert d["checks"]["tally_range_flag"] == 0 and abs(d["checks"]["absorbed_weight_per_photon"] - 1.0) < 1e-4
