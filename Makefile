@@ -61,8 +61,12 @@ oracle:
 	$(MAKE) -C oracle all
 	@if [ -d /root/reference ]; then $(MAKE) -C oracle ref; fi
 
+# CPU-side tests here; the GPU-side ones need a B200 (python -m pytest tests -m gpu)
+test: all
+	python -m pytest tests -q -m "not gpu"
+
 clean:
 	rm -rf $(LIBDIR) $(BINDIR)
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib host configs oracle clean
+.PHONY: all lib host configs oracle test clean
