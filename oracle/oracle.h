@@ -53,7 +53,7 @@ void orc_seed(int kind, unsigned seed);
 uint64_t orc_run_batch(const orc_optics* o, orc_photon_fn fn, int rng_kind, unsigned seed, uint64_t n_photons,
                        uint32_t chunk, double* heat, double* heat2, float* heat_f, float* heat2_f);
 
-/* ---- stream_replay.c : CPU replay of the product's stream "tmc-stream-3" ---- */
+/* ---- stream_replay.c : CPU replay of the product's stream "tmc-stream-4" ---- */
 
 typedef struct orc_fx_scales {
     uint32_t weight_one;     /* fixed-point value of weight 1.0 (= 2^heat_shift)        */
@@ -73,8 +73,10 @@ void orc_fx_plan(const orc_optics* o, orc_fx_scales* s);
 uint32_t orc_generation_plan(const orc_optics* o, uint32_t max_gen, uint32_t* first_event, uint32_t* n_events,
                              uint32_t* w_start);
 
-/* word -> step length [mfp] (bits 10..31) and word -> cos(theta) (bits 1..9) of the stream */
+/* word -> step length [mfp] (bits 9..31), its uniform variate xi, and word -> cos(theta) (bits 8..15) */
 float orc_step_of_word(uint32_t v);
+double orc_xi_of_word(uint32_t v);
+void orc_step_moments(double out[2]);   /* exact enumeration of the 2^23 step values: E[t], E[t^2] */
 float orc_costheta_of_word(uint32_t v);
 
 /* Replay photons [first, first+n) of stream `seed`; ADD into u64 heat_fx/heat2_fx[shells].

@@ -69,6 +69,9 @@ def lib() -> C.CDLL:
         l.orc_replay_mode.argtypes = [C.POINTER(Optics), C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         l.orc_step_of_word.restype = C.c_float
         l.orc_step_of_word.argtypes = [C.c_uint32]
+        l.orc_xi_of_word.restype = C.c_double
+        l.orc_xi_of_word.argtypes = [C.c_uint32]
+        l.orc_step_moments.argtypes = [C.c_void_p]
         l.orc_costheta_of_word.restype = C.c_float
         l.orc_costheta_of_word.argtypes = [C.c_uint32]
         l.orc_generation_plan.restype = C.c_uint32

@@ -1,17 +1,20 @@
 /* oracle/stream_replay.c — TEST INFRASTRUCTURE ONLY (see oracle/README.md).
  *
  * CPU replay of the PRODUCT's random stream and fixed-point tally arithmetic
- * ("tmc-stream-3"), restated independently in scalar C with libm
- * (log2f / sqrtf, cos / sin in double for the azimuth table) standing in for the GPU's MUFU
- * approximations.
+ * ("tmc-stream-4"), restated independently in scalar C with libm
+ * (log2f / sqrtf, cos / sin / sqrt in double for the direction table) standing in for the GPU's
+ * MUFU approximations.
  *
  * Stream layout: photon i draws Philox4x32-R(counter = (i_lo, i_hi, block, 0), key = seed);
- * one block = four words = THREE scatter events of 42 bits each.  Event e >= 1 of a photon is
- * slot e % 3 of block e / 3 and uses word[slot] plus bits [10*slot, 10*slot+10) of word[3];
- * pseudo-event 0 (block 0, slot 0) is the photon's roulette fate word.  Inside an event word v:
- *   bits 10..31  step:      xi = 2 * (1.5 - f), f = 1 + (v >> 10) * 2^-23      (22 bits)
- *   bits  1..9   cos theta: (2k + 1) / 512 - 1                                 ( 9 bits, midpoints)
- *   word[3] slice: azimuth index into a 1024-entry (cos, sin) table            (10 bits)
+ * one block = four words = FOUR scatter events, one word each.  Event e >= 1 of a photon is
+ * word e % 4 of block e / 4; pseudo-event 0 (block 0, word 0) is the photon's roulette fate
+ * word.  Inside an event word v:
+ *   bits  9..31  step:      xi = (m + 1/2) * 2^-23, m = v >> 9                 (23 bits, midpoints)
+ *   bits  8..15  cos theta: (2k + 1) / 256 - 1                                 ( 8 bits, midpoints)
+ *   bits  0..7   azimuth:   phi = 2 pi k / 256                                 ( 8 bits)
+ * (the polar index shares bits 9..15 with the step's seven lowest mantissa bits.)
+ * The direction table holds float(-ln2 cos theta), float(-ln2 sin theta), float(cos phi),
+ * float(sin phi), computed in double; the step enters as L = log2(xi) <= 0.
  * The direction is drawn at the START of an event (spin, then hop), so no direction is carried
  * from one event to the next; the first event's direction is the isotropic launch direction.
  *
@@ -86,7 +89,7 @@ void orc_fx_plan(const orc_optics* o, orc_fx_scales* s)
 
 typedef union { uint32_t u; float f; } bits32;
 
-#define AZIMUTH_ENTRIES 1024u
+#define DIR_ENTRIES 256u
 
 /* Deterministic weight schedule: every photon of generation g (= number of
  * roulettes survived) starts it with the same weight and needs the same number of events
@@ -113,16 +116,42 @@ uint32_t orc_generation_plan(const orc_optics* o, uint32_t max_gen, uint32_t* fi
 }
 
 /* The two word -> variate mappings of the stream, exported for edge-case tests. */
+static const float ONE_MINUS_HALF_ULP = 0.999999940395355224609375f;   /* 1 - 2^-24 */
+
+/* L = log2(xi), xi = (m + 1/2) 2^-23, m = v >> 9: exact in float (Sterbenz) */
+static float log2_xi_of_word(uint32_t v)
+{
+    bits32 b;
+    b.u = 0x3F800000u | (v >> 9);
+    return log2f(b.f - ONE_MINUS_HALF_ULP);
+}
+
 float orc_step_of_word(uint32_t v)
 {
-    bits32 fb;
-    fb.u = 0x3F800000u | (v >> 10);
-    return fmaf(log2f(1.5f - fb.f), -0.693147182464599609375f, -0.693147182464599609375f);
+    return -0.693147182464599609375f * log2_xi_of_word(v);
+}
+
+double orc_xi_of_word(uint32_t v)
+{
+    return ((double)(v >> 9) + 0.5) / 8388608.0;
+}
+
+/* E[t] and E[t^2] over ALL 2^23 step mantissas, through the float path the replay uses */
+void orc_step_moments(double out[2])
+{
+    double m1 = 0.0, m2 = 0.0;
+    for (uint32_t m = 0; m < (1u << 23); ++m) {
+        const double t = (double)orc_step_of_word(m << 9);
+        m1 += t;
+        m2 += t * t;
+    }
+    out[0] = m1 / 8388608.0;
+    out[1] = m2 / 8388608.0;
 }
 
 float orc_costheta_of_word(uint32_t v)
 {
-    return fmaf((float)(8388608u + ((v & 0x3FEu) | 1u)), 0.001953125f, -16385.0f);
+    return (float)((2.0 * (double)((v >> 8) & 255u) + 1.0) / 256.0 - 1.0);
 }
 
 uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n,
@@ -145,15 +174,20 @@ uint64_t orc_replay_mode(const orc_optics* o, uint32_t rounds, uint64_t seed, ui
     const uint64_t half = s.heat2_rshift ? ((uint64_t)1 << (s.heat2_rshift - 1)) : 0;
     const float LN2 = 0.693147182464599609375f;          /* float(ln 2)       */
     const uint32_t FATE_SURVIVE = 429496729u;            /* floor(0.1 * 2^32) */
-    static float az_cos[AZIMUTH_ENTRIES], az_sin[AZIMUTH_ENTRIES];
-    static int az_ready = 0;
-    if (!az_ready) {
-        for (uint32_t i = 0; i < AZIMUTH_ENTRIES; ++i) {
-            const double phi = 6.283185307179586476925 * (double)i / (double)AZIMUTH_ENTRIES;
-            az_cos[i] = (float)cos(phi);
-            az_sin[i] = (float)sin(phi);
+    static float pol_c[DIR_ENTRIES], pol_s[DIR_ENTRIES], az_cos[DIR_ENTRIES], az_sin[DIR_ENTRIES];
+    static int dir_ready = 0;
+    if (!dir_ready) {
+        const double ln2 = 0.693147180559945309417232;
+        for (uint32_t k = 0; k < DIR_ENTRIES; ++k) {
+            const double ct = (2.0 * (double)k + 1.0) / (double)DIR_ENTRIES - 1.0;
+            const double st = sqrt(1.0 - ct * ct);
+            const double phi = 6.283185307179586476925 * (double)k / (double)DIR_ENTRIES;
+            pol_c[k] = (float)(-ln2 * ct);
+            pol_s[k] = (float)(-ln2 * st);
+            az_cos[k] = (float)cos(phi);
+            az_sin[k] = (float)sin(phi);
         }
-        az_ready = 1;
+        dir_ready = 1;
     }
     uint64_t events = 0;
 
@@ -164,8 +198,8 @@ uint64_t orc_replay_mode(const orc_optics* o, uint32_t rounds, uint64_t seed, ui
         uint32_t r[4] = { 0, 0, 0, 0 };
         uint32_t have_blk = 0xFFFFFFFFu, fate = 0;
         for (uint32_t e = 0;; ++e) {
-            /* pseudo-event 0 is the fate word; event e >= 1 is slot e % 3 of block e / 3 */
-            const uint32_t blk = e / 3u, slot = e % 3u;
+            /* pseudo-event 0 is the fate word; event e >= 1 is word e % 4 of block e / 4 */
+            const uint32_t blk = e / 4u, slot = e % 4u;
             if (blk != have_blk) {
                 const uint32_t ctr[4] = { (uint32_t)p, (uint32_t)(p >> 32), blk, 0u };
                 orc_philox4x32(rounds, ctr, key, r);
@@ -175,28 +209,23 @@ uint64_t orc_replay_mode(const orc_optics* o, uint32_t rounds, uint64_t seed, ui
                 fate = r[0];
                 continue;
             }
-            const uint32_t v = r[slot], az = (r[3] >> (10u * slot)) & 1023u;
+            const uint32_t v = r[slot], kp = (v >> 8) & 255u, ka = v & 255u;
             ++events;
-            /* spin (photon.c:35-43, sampled directly, BEFORE the hop so that no direction is
-             * carried between events): cos(theta) = (2k+1)/512 - 1 from bits 1..9, azimuth
-             * from a 1024-entry table indexed by 10 bits of word 3 */
-            /* hop (photon.c:21-24): xi = 2 * (1.5 - f), f = 1 + (v >> 10) * 2^-23 */
-            bits32 fb;
-            fb.u = 0x3F800000u | (v >> 10);
-            const float t = fmaf(log2f(1.5f - fb.f), -LN2, -LN2);
+            /* hop (photon.c:21-24): L = log2(xi), t = -ln2 L; -ln2 is folded into the polar table */
+            const float L = log2_xi_of_word(v);
             float rad;
-            if (mode == 1) { /* reduced radial walk: x holds the radius, 2 mu = (2k+1)/256 - 2 */
-                const float mu2 = fmaf((float)(8388608u + ((v & 0x3FEu) | 1u)), 0.00390625f, -32770.0f);
-                const float r2 = fmaf(t * x, mu2, fmaf(t, t, x * x));
+            if (mode == 1) { /* reduced radial walk: x holds the radius, mu = cos(theta_k) */
+                const float t = L * -LN2, tmu = L * pol_c[kp];
+                const float r2 = fmaf(x + x, tmu, fmaf(t, t, x * x));
                 rad = sqrtf(r2 > 0.0f ? r2 : 0.0f);
                 x = rad;
             } else {
-                const float ct = fmaf((float)(8388608u + ((v & 0x3FEu) | 1u)), 0.001953125f, -16385.0f);
-                const float st = sqrtf(fmaf(-ct, ct, 1.0f));
-                const float ts = t * st;
-                x = fmaf(t, ct, x);
-                y = fmaf(ts, az_cos[az], y);
-                z = fmaf(ts, az_sin[az], z);
+                /* spin (photon.c:35-43, sampled directly, BEFORE the hop so that no direction is
+                 * carried between events) and move (photon.c:22-24) */
+                const float ts = L * pol_s[kp];
+                x = fmaf(L, pol_c[kp], x);
+                y = fmaf(ts, az_cos[ka], y);
+                z = fmaf(ts, az_sin[ka], z);
                 /* drop (photon.c:26-32) */
                 rad = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
             }

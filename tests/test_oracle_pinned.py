@@ -132,7 +132,7 @@ def test_libc_rand_biases_the_reference_itself():
 
 
 def test_replay_agrees_with_reference_walk_on_sound_rng(orc):
-    """tmc-stream-3 (Philox, direct direction sampling, fixed-point weights) vs the reference walk
+    """tmc-stream-4 (Philox, direct direction sampling, fixed-point weights) vs the reference walk
     (photon_port.c: rejection sampling, float weights) on xoshiro256**: every shell within 4 sigma."""
     from stats import batch_means_z
 
@@ -180,13 +180,22 @@ def test_word_to_variate_mappings_have_no_singularities(orc):
     (photon.c:21-23); `sqrtf((1 - u*u) / t)` divides by zero for t == 0 (photon.c:42-43).
     The stream's mappings are finite and well-centred for every input word."""
     l = orc.lib()
-    assert l.orc_step_of_word(0x00000000) == 0.0                        # xi = 1
-    assert l.orc_step_of_word(0x000003FF) == 0.0                        # the low 10 bits are not step bits
-    longest = l.orc_step_of_word(0xFFFFFFFF)
-    assert abs(longest - 22 * np.log(2.0)) < 1e-5 and np.isfinite(longest)   # xi = 2^-22: 15.25 mean free paths
+    shortest, longest = l.orc_step_of_word(0xFFFFFFFF), l.orc_step_of_word(0x00000000)
+    assert 0.0 < shortest < 1e-7                                        # xi = 1 - 2^-24: never exactly 0
+    assert l.orc_step_of_word(0x000001FF) == longest                    # the low 9 bits are not step bits
+    assert abs(longest - 24 * np.log(2.0)) < 1e-5 and np.isfinite(longest)   # xi = 2^-24: 16.6 mean free paths
+    assert l.orc_xi_of_word(0) == 2.0 ** -24 and l.orc_xi_of_word(0xFFFFFFFF) == 1.0 - 2.0 ** -24
+    # midpoint rule: the EXACT mean over all 2^23 step values (float path of the replay) is 1 to
+    # 1e-6 (analytically -0.35 * 2^-23 = -4e-8), and E[t^2] = 2 to 1e-5 (reference photon.c:21)
+    mom = np.zeros(2)
+    l.orc_step_moments(mom.ctypes.data)
+    assert abs(mom[0] - 1.0) < 1e-6, mom
+    assert abs(mom[1] - 2.0) < 1e-5, mom
+    xi = (np.arange(1 << 23, dtype=np.float64) + 0.5) / (1 << 23)       # the same in exact arithmetic
+    assert abs(-np.log(xi).mean() - 1.0) < 1e-7
     steps = np.array([l.orc_step_of_word(int(v)) for v in np.linspace(0, 2**32 - 1, 20001).astype(np.uint64)])
-    assert (np.diff(steps) >= 0).all() and abs(steps.mean() - 1.0) < 2e-3       # monotone, E[t] = 1
-    cos = np.array([l.orc_costheta_of_word(k << 1) for k in range(512)], np.float64)
-    assert np.array_equal(cos, (2 * np.arange(512) + 1) / 512.0 - 1.0)          # exact midpoints
-    assert cos.sum() == 0.0 and abs((cos**2).mean() * 3 - 1.0) < 4e-6 and np.abs(cos).max() < 1.0
-    assert l.orc_costheta_of_word(0xFFFFFC01) == cos[0]                          # only bits 1..9 matter
+    assert (np.diff(steps) <= 0).all()                                            # monotone in the word
+    cos = np.array([l.orc_costheta_of_word(k << 8) for k in range(256)], np.float64)
+    assert np.array_equal(cos, (2 * np.arange(256) + 1) / 256.0 - 1.0)          # exact midpoints
+    assert cos.sum() == 0.0 and abs((cos**2).mean() * 3 - 1.0) < 1.6e-5 and np.abs(cos).max() < 1.0
+    assert l.orc_costheta_of_word(0xFFFF00FF) == cos[0]                          # only bits 8..15 matter

@@ -190,28 +190,40 @@ int deposit_table(int device, const Plan& pl, const uint2** out)
     uint2* d = nullptr;
     CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(uint2)));
     CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize());   // see directions_table(): the kernel's stream is not ordered after this copy
     g_deposit_tables.push_back(DepositTable{ device, pl.sc.absorb_q32, pl.weight_one, pl.sc.heat2_rshift, pl.sc.roulette_thr, d });
     *out = d;
     return TMC_OK;
 }
 
 using KernelFn = void (*)(const WalkArgs);
+#ifndef TMC_PPL
+#define TMC_PPL 2
+#endif
+constexpr int kPhotonsPerLane = TMC_PPL;   // photons per lane of every compiled kernel variant
+
+// default block shapes (measured best, profiles/): lane-private tallies / one histogram per block
+#ifndef TMC_DEFAULT_BLOCK_PRIVATE
+#define TMC_DEFAULT_BLOCK_PRIVATE 512
+#endif
+#ifndef TMC_DEFAULT_BLOCK_PLAIN
+#define TMC_DEFAULT_BLOCK_PLAIN 1024
+#endif
 
 // Block shapes: threads per block (two photons per thread) x the residency the register
-// budget is compiled for.  A block needs 8 KB (azimuth table) + its tallies (SHELLS * 256 B
-// lane-private, else (SHELLS + 31) * 8 B) of shared memory.
+// budget is compiled for.  A block needs 64 KB (direction table) + its tallies (SHELLS * 256 B
+// lane-private, else (SHELLS + 31) * 8 B) of shared memory, so at most 3 blocks fit an SM.
 template <int ROUNDS, bool LANE_PRIVATE>
 KernelFn kernel_for_block(int block, int per_sm)
 {
     // (threads per block, blocks per SM the register budget is compiled for)
     switch (block * 8 + per_sm) {
-    case 128 * 8 + 4: return tmc::photon_walk_kernel<ROUNDS, 128, 4, LANE_PRIVATE>;   // 128 registers
-    case 256 * 8 + 2: return tmc::photon_walk_kernel<ROUNDS, 256, 2, LANE_PRIVATE>;   // 128
-    case 256 * 8 + 3: return tmc::photon_walk_kernel<ROUNDS, 256, 3, LANE_PRIVATE>;   //  80
-    case 256 * 8 + 4: return tmc::photon_walk_kernel<ROUNDS, 256, 4, LANE_PRIVATE>;   //  64
-    case 512 * 8 + 1: return tmc::photon_walk_kernel<ROUNDS, 512, 1, LANE_PRIVATE>;   // 128
-    case 512 * 8 + 2: return tmc::photon_walk_kernel<ROUNDS, 512, 2, LANE_PRIVATE>;   //  64
-    case 1024 * 8 + 1: return tmc::photon_walk_kernel<ROUNDS, 1024, 1, LANE_PRIVATE>; //  64
+    case 128 * 8 + 3: return tmc::photon_walk_kernel<ROUNDS, 128, 3, LANE_PRIVATE, false, kPhotonsPerLane>;   // 168 registers
+    case 256 * 8 + 2: return tmc::photon_walk_kernel<ROUNDS, 256, 2, LANE_PRIVATE, false, kPhotonsPerLane>;   // 128
+    case 256 * 8 + 3: return tmc::photon_walk_kernel<ROUNDS, 256, 3, LANE_PRIVATE, false, kPhotonsPerLane>;   //  80
+    case 512 * 8 + 1: return tmc::photon_walk_kernel<ROUNDS, 512, 1, LANE_PRIVATE, false, kPhotonsPerLane>;   // 128
+    case 768 * 8 + 1: return tmc::photon_walk_kernel<ROUNDS, 768, 1, LANE_PRIVATE, false, kPhotonsPerLane>;   //  80
+    case 1024 * 8 + 1: return tmc::photon_walk_kernel<ROUNDS, 1024, 1, LANE_PRIVATE, false, kPhotonsPerLane>; //  64
     default: return nullptr;
     }
 }
@@ -220,8 +232,8 @@ KernelFn kernel_for_block(int block, int per_sm)
 template <int ROUNDS>
 KernelFn radial_kernel(int block, int per_sm, bool lane_private)
 {
-    if (lane_private && block == 512 && per_sm == 1) return tmc::photon_walk_kernel<ROUNDS, 512, 1, true, true>;
-    if (!lane_private && block == 1024 && per_sm == 1) return tmc::photon_walk_kernel<ROUNDS, 1024, 1, false, true>;
+    if (lane_private && block == TMC_DEFAULT_BLOCK_PRIVATE && per_sm == 1) return tmc::photon_walk_kernel<ROUNDS, TMC_DEFAULT_BLOCK_PRIVATE, 1, true, true, kPhotonsPerLane>;
+    if (!lane_private && block == TMC_DEFAULT_BLOCK_PLAIN && per_sm == 1) return tmc::photon_walk_kernel<ROUNDS, TMC_DEFAULT_BLOCK_PLAIN, 1, false, true, kPhotonsPerLane>;
     return nullptr;
 }
 
@@ -239,16 +251,17 @@ KernelFn pick_kernel(int rounds, int block, int per_sm, bool lane_private, bool 
 int default_blocks_per_sm(int block)
 {
     switch (block) {
-    case 128: return 4;
+    case 128: return 3;
     case 256: return 2;
-    case 512: return 1;
     default: return 1;
     }
 }
 
-// (cos, sin)(2 pi i / 1024) in float, computed in double on the host and uploaded once per
-// device; every block stages it into shared memory (walk_kernel.cuh: spin()).
-const float2* g_azimuth[64] = {};
+// The direction table (walk_kernel.cuh: event()): 256 polar entries (-ln2 cos, -ln2 sin)(theta_k) with
+// cos(theta_k) = (2k + 1)/256 - 1 (midpoints: odd moments vanish, E[cos^2] = 1/3 (1 - 2^-16)), then 256
+// azimuth entries (cos, sin)(2 pi k / 256); computed in double, rounded once, uploaded once per
+// device; every block stages 16 copies of it into shared memory.  -ln2 turns log2(xi) into the step.
+const float2* g_directions[64] = {};
 
 // Survivor-queue scratch (walk_kernel.cuh): kQueueBytesPerWarp per warp of the largest grid, one
 // buffer per device and stream (two launches on one stream are ordered, so they can share it).
@@ -282,21 +295,28 @@ int queue_scratch(int device, cudaStream_t stream, size_t bytes, uint32_t** out)
     return TMC_OK;
 }
 
-int azimuth_table(int device, const float2** out)
+int directions_table(int device, const float2** out)
 {
     if (device < 0 || device >= 64) return fail(TMC_ERR_BAD_ARG, "device %d out of range", device);
-    if (!g_azimuth[device]) {
-        std::vector<float2> h(tmc::kAzimuthEntries);
-        for (int i = 0; i < tmc::kAzimuthEntries; ++i) {
-            const double phi = 6.283185307179586476925 * static_cast<double>(i) / tmc::kAzimuthEntries;
-            h[i] = make_float2(static_cast<float>(std::cos(phi)), static_cast<float>(std::sin(phi)));
+    if (!g_directions[device]) {
+        std::vector<float2> h(2 * tmc::kDirEntries);
+        const double ln2 = 0.693147180559945309417232;
+        for (int k = 0; k < tmc::kDirEntries; ++k) {
+            const double ct = (2.0 * k + 1.0) / tmc::kDirEntries - 1.0;
+            const double st = std::sqrt(1.0 - ct * ct);
+            h[k] = make_float2(static_cast<float>(-ln2 * ct), static_cast<float>(-ln2 * st));
+            const double phi = 6.283185307179586476925 * static_cast<double>(k) / tmc::kDirEntries;
+            h[tmc::kDirEntries + k] = make_float2(static_cast<float>(std::cos(phi)), static_cast<float>(std::sin(phi)));
         }
         float2* d = nullptr;
         CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(float2)));
         CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        g_azimuth[device] = d;
+        // a pageable cudaMemcpy may return once the data is staged; the walk runs on non-blocking
+        // streams that are not ordered after the legacy stream, so wait for the DMA here (one-off)
+        CUDA_TRY(cudaDeviceSynchronize());
+        g_directions[device] = d;
     }
-    *out = g_azimuth[device];
+    *out = g_directions[device];
     return TMC_OK;
 }
 
@@ -375,7 +395,7 @@ int configure_launch(const tmc_params* p, const Plan& pl, int device_sms, uint64
     if (g.opt.tally_layout == 2 && !lane_private)
         return fail(TMC_ERR_BAD_ARG, "SHELLS=%u is too large for lane-private tallies (max %u)", p->shells, tmc::kLanePrivateMaxShells);
     int block = g.opt.block_threads;
-    if (block == 0) block = lane_private ? 512 : 1024;   // measured best: profiles/r01_*sweep*
+    if (block == 0) block = lane_private ? TMC_DEFAULT_BLOCK_PRIVATE : TMC_DEFAULT_BLOCK_PLAIN;
     const size_t smem = tmc::walk_smem_bytes(p->shells, lane_private, static_cast<uint32_t>(block));
     if (smem > 227u * 1024u)
         return fail(TMC_ERR_BAD_ARG, "SHELLS=%u with %d-thread blocks needs %zu B of shared memory per block (> 227 KB)", p->shells, block, smem);
@@ -385,7 +405,7 @@ int configure_launch(const tmc_params* p, const Plan& pl, int device_sms, uint64
     if (want > smem_fit) want = smem_fit;
     KernelFn fn = nullptr;
     for (int c = want; c >= 1 && !fn; --c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private, g.opt.walk_mode == 1);   // largest budget <= want
-    for (int c = want + 1; c <= 4 && !fn; ++c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private, g.opt.walk_mode == 1);   // else the next one
+    for (int c = want + 1; c <= 3 && !fn; ++c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private, g.opt.walk_mode == 1);   // else the next one
     if (!fn)
         return fail(TMC_ERR_BAD_ARG, "no kernel for philox_rounds=%d block_threads=%d blocks_per_sm=%d walk_mode=%d", g.opt.philox_rounds,
                     block, g.opt.blocks_per_sm, g.opt.walk_mode);
@@ -396,38 +416,43 @@ int configure_launch(const tmc_params* p, const Plan& pl, int device_sms, uint64
     if (g.opt.blocks_per_sm > 0 && g.opt.blocks_per_sm < per_sm) per_sm = g.opt.blocks_per_sm;
     uint64_t grid = static_cast<uint64_t>(device_sms) * per_sm;
     const uint64_t warps = static_cast<uint64_t>(block) / 32u;
-    const uint64_t needed = ((count + 63) / 64 + warps - 1) / warps;   // cohorts of 64 photons, one per warp
+    const uint64_t cohort = 32ull * kPhotonsPerLane;
+    const uint64_t needed = ((count + cohort - 1) / cohort + warps - 1) / warps;   // cohorts of photons, one per warp
     if (needed < grid) grid = needed ? needed : 1;
     uint32_t flush = flush_override ? flush_override : static_cast<uint32_t>(g.opt.flush_iters);
     if (flush == 0) {
-        // Philox blocks (3 events for each of a warp's 64 photons) between two drains of the u32
-        // block histograms; deposits are < 2^21.
-        // the largest amount one event adds to a heat or to a heat2 word
+        // Philox blocks (kEventsPerBlock events for each of a warp's photons) between two drains of
+        // the u32 block histograms.  d0 = the largest amount one event adds to a word.
         const uint64_t dep0 = (static_cast<uint64_t>(pl.weight_one) * pl.sc.absorb_q32 + 0x80000000ull) >> 32;
         const uint64_t dep20 = (dep0 * dep0 + pl.heat2_half) >> pl.sc.heat2_rshift;
         const double d0 = static_cast<double>(dep0 > dep20 ? dep0 : dep20);
+        // A slice is drained once per `warps` drain calls of the block.  Between two drains of one slice
+        // every warp walks at most 2 * flush blocks (its own calls may fall anywhere in the interval),
+        // i.e. ev = 2 * flush * kEventsPerBlock events per photon slot.
+        const double ev_per_flush = 2.0 * tmc::kEventsPerBlock;
+        const double ppl = static_cast<double>(kPhotonsPerLane);
         if (lane_private) {
-            // A (shell, lane) slot only ever sees the 2 photons per warp of its own lane.  Two hard
-            // bounds on what they can add to one u32 word between two drains.  A slice is drained
-            // once per `warps` drain calls; in between a warp walks at most 2 * flush blocks (its own
-            // calls may fall anywhere in the interval), i.e. 6 * flush events per photon slot:
-            //  (a) every event deposits at most the first deposit d0: 12 * warps * flush * d0 < 2^32;
+            // A (shell, lane) word only ever sees the ppl photon slots per warp of its own lane.  Two
+            // hard bounds on what they can add to it between two drains:
+            //  (a) every event deposits at most d0:  warps * ppl * ev_per_flush * flush * d0 < 2^32;
             //  (b) a photon deposits at most its whole weight 2^heat_shift in its life, and at most
-            //      ceil(6 * flush / K0) + 1 lives per photon slot touch the interval.
+            //      ceil(ev_per_flush * flush / K0) + 1 lives per photon slot touch the interval.
             // Either suffices, so the larger interval is taken; the 2^31 check stays as a tripwire.
-            const double by_event = 4294967296.0 / (12.0 * static_cast<double>(warps) * (d0 + 1.0));
-            const double lives = 4294967296.0 / (2.0 * static_cast<double>(warps) * static_cast<double>(pl.weight_one)) - 1.0;
-            const double by_life = lives >= 2.0 ? (std::floor(lives) - 1.0) * static_cast<double>(pl.gen[0].n_events) / 6.0 : 0.0;
+            const double by_event = 4294967296.0 / (ev_per_flush * ppl * static_cast<double>(warps) * (d0 + 1.0));
+            const double lives = 4294967296.0 / (ppl * static_cast<double>(warps) * static_cast<double>(pl.weight_one)) - 1.0;
+            const double by_life = lives >= 2.0 ? (std::floor(lives) - 1.0) * static_cast<double>(pl.gen[0].n_events) / ev_per_flush : 0.0;
             double blocks = by_event > by_life ? by_event : by_life;
             if (blocks > 512.0) blocks = 512.0;
             flush = blocks < 1.0 ? 1u : static_cast<uint32_t>(blocks);
         } else {
-            // One histogram per block: the busiest shell takes at most the first-collision share
-            // 1 - exp(-1/shells_per_mfp) <= 1/shells_per_mfp of a block's events (x2 margin here, and
-            // the target is 2^31, half of what would wrap; the 2^31 check catches the rest).
+            // One histogram per block, every photon of the block can hit the same word.  The busiest
+            // shell takes at most the first-collision share 1 - exp(-1/shells_per_mfp) <= 1/shells_per_mfp
+            // of a block's events in expectation (x2 margin, and the target is 2^31, half of what would
+            // wrap; the 2^31 check catches the rest: tmc_photons* repeat the range with a shorter interval,
+            // callers of tmc_photons_device must test the flag word, e.g. with tmc_device_tallies_check).
             double share = 2.0 / static_cast<double>(shells_per_mfp_of(p));
             if (share > 1.0) share = 1.0;
-            const double blocks = 2147483648.0 / (64.0 * static_cast<double>(warps) * 6.0 * share * (d0 + 1.0));
+            const double blocks = 2147483648.0 / (32.0 * ppl * static_cast<double>(warps) * ev_per_flush * share * (d0 + 1.0));
             flush = blocks > 64.0 ? 64u : (blocks < 1.0 ? 1u : static_cast<uint32_t>(blocks));
         }
         if (flush < 1u) flush = 1u;
@@ -450,7 +475,7 @@ int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t fi
     WalkArgs a;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
-    int rc = azimuth_table(dev, &a.azimuth);
+    int rc = directions_table(dev, &a.directions);
     if (rc) return rc;
     tmc::philox_expand_key(seed, &a.keys);
     a.tallies = d_buf;
@@ -623,6 +648,8 @@ int run_fx(const tmc_params* p, uint64_t seed, uint64_t first, uint64_t n, uint6
         for (int attempt = 0;; ++attempt) {
             rc = run_range(p, pl, seed, first + done, todo, flush_override, sum, &kernel_ms);
             if (rc) return rc;
+            if (sum[2ull * p->shells + 3] != 0ull)
+                return fail(TMC_ERR_CUDA, "internal: the block's shared-memory window does not start where walk_kernel.cuh assumes");
             if (sum[2ull * p->shells + 2] == 0ull) break;
             if (attempt == 3 || g.info.flush_iters <= 1u)
                 return fail(TMC_ERR_TALLY_RANGE, "a shared tally exceeded 2^31 within %u iterations", g.info.flush_iters);
@@ -659,7 +686,7 @@ void accumulate_float(const tmc_params* p, const Plan& pl, const uint64_t* heat_
 extern "C" {
 
 int tmc_abi_version(void) { return TMC_ABI_VERSION; }
-const char* tmc_version(void) { return "tiny_mc_b200 0.3 (sm_100a, stream tmc-stream-3)"; }
+const char* tmc_version(void) { return "tiny_mc_b200 0.4 (sm_100a, stream tmc-stream-4)"; }
 const char* tmc_last_error(void) { return g.err.c_str(); }
 int tmc_device_count(void) { return g.inited ? static_cast<int>(g.devs.size()) : 0; }
 
@@ -676,11 +703,11 @@ int tmc_finalize(void)
     g.devs.clear();
     // cached tables and scratch (recreated lazily by the next call on that device)
     for (int d = 0; d < 64; ++d)
-        if (g_azimuth[d]) {
+        if (g_directions[d]) {
             cudaSetDevice(d);
             cudaDeviceSynchronize();
-            cudaFree(const_cast<float2*>(g_azimuth[d]));
-            g_azimuth[d] = nullptr;
+            cudaFree(const_cast<float2*>(g_directions[d]));
+            g_directions[d] = nullptr;
         }
     for (DepositTable& t : g_deposit_tables) {
         cudaSetDevice(t.device);
@@ -757,11 +784,11 @@ int tmc_set_option(const char* name, long long value)
         if (value != 7 && value != 10) return fail(TMC_ERR_BAD_ARG, "philox_rounds must be 10 (default) or 7");
         g.opt.philox_rounds = static_cast<int>(value);
     } else if (n == "block_threads") {
-        if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024)
-            return fail(TMC_ERR_BAD_ARG, "block_threads must be 0, 128, 256, 512 or 1024");
+        if (value != 0 && value != 128 && value != 256 && value != 512 && value != 768 && value != 1024)
+            return fail(TMC_ERR_BAD_ARG, "block_threads must be 0, 128, 256, 512, 768 or 1024");
         g.opt.block_threads = static_cast<int>(value);
     } else if (n == "blocks_per_sm") {
-        if (value < 0 || value > 4) return fail(TMC_ERR_BAD_ARG, "blocks_per_sm must be 0..4");
+        if (value < 0 || value > 3) return fail(TMC_ERR_BAD_ARG, "blocks_per_sm must be 0..3");
         g.opt.blocks_per_sm = static_cast<int>(value);
     } else if (n == "flush_iters") {
         if (value < 0 || value > 4096) return fail(TMC_ERR_BAD_ARG, "flush_iters must be 0..4096");

@@ -19,10 +19,10 @@
 //    regenerates 64 fresh photons in place (or, when 64 survivors have accumulated, a full
 //    cohort of them).  Generations beyond the second (1e-3 of the photons) continue in place
 //    with the dead lanes masked.
-//  * Random stream "tmc-stream-3": Philox4x32-R keyed by the seed, counter = (photon index,
-//    block).  One Philox block = THREE events of 42 bits; event e of a photon is slot e % 3 of
-//    block e / 3, pseudo-event 0 is the roulette fate word.  A photon's trajectory depends on
-//    (seed, photon index) only.
+//  * Random stream "tmc-stream-4": Philox4x32-R keyed by the seed, counter = (photon index,
+//    block).  One Philox block = FOUR events, one 32-bit word each; event e of a photon is word
+//    e % 4 of block e / 4, pseudo-event 0 is the roulette fate word.  A photon's trajectory
+//    depends on (seed, photon index) only.
 //  * Deposits are exact integers (32-bit fixed-point weights); tallies are u32 shared-memory
 //    histograms privatised per block AND per lane ([shell][heat|heat2][lane]: every lane of a
 //    warp owns its own bank, an ATOMS.ADD is always one conflict-free wavefront, also for the
@@ -30,10 +30,10 @@
 //    tallies => the result does not depend on thread/block/GPU count or on atomic ordering.
 //    Grids too fine for per-lane copies use one u32 histogram per block plus 32 per-lane
 //    slots for the overflow bin.
-//  * Per event and photon: 3 MUFU (lg2 for the step, sqrt for sin(theta), sqrt for the
-//    radius), 12 FP32 operations (8 of them issued as 4 packed FFMA2 / FMUL2 / FADD2 for the
-//    two photons of a lane), 2 shared atomics, one LDS.64 for the azimuth (cos, sin) table
-//    and a third of a Philox block: 38.6 warp instructions per event in all (ncu).
+//  * Per event and photon: 2 MUFU (lg2 for the step, sqrt for the radius), 10 FP32 operations,
+//    2 shared atomics, two conflict-free LDS.64 for the direction (polar and azimuth tables,
+//    each replicated over 16 bank pairs so that lane l only ever reads bank pair l % 16) and a
+//    quarter of a Philox block.
 #pragma once
 #include <cstdint>
 
@@ -45,8 +45,19 @@
 
 namespace tmc {
 
-constexpr int kAzimuthEntries = 1024;                       // (cos, sin)(2 pi i / 1024): 8 KB
-constexpr uint32_t kAzimuthBytes = kAzimuthEntries * 8u;
+constexpr uint32_t kEventsPerBlock = 4u;                    // one 32-bit Philox word per scatter event
+constexpr int kDirEntries = 256;                            // polar midpoints / azimuths (8 bits each)
+// Direction table in shared memory: row k (256 B) = 16 copies of (-ln2 cos, -ln2 sin)(theta_k) followed
+// by 16 copies of (cos, sin)(phi_k).  Lane l reads copy l % 16: an LDS.64 touches every bank pair once
+// per half-warp, whatever the 32 random row numbers are (2 wavefronts, the minimum for 256 B).
+constexpr uint32_t kDirTableBytes = kDirEntries * 256u;     // 64 KB
+// Shared-memory map of a block, in ABSOLUTE addresses of the CTA's shared window, so that every
+// LDS / ATOMS of the event loop carries its base as an immediate ([R + imm]) and the index register
+// comes straight out of one PRMT: user shared memory starts at 0x400 (CUDA reserves the first KB),
+// the table sits at 0x800, the histograms behind it.  The kernel checks the assumption at start-up.
+constexpr uint32_t kSmemUserBase = 0x400u;
+constexpr uint32_t kSmemTableAbs = 0x800u;
+constexpr uint32_t kSmemBinsAbs = kSmemTableAbs + kDirTableBytes;
 constexpr int kMaxGenerations = 24;                         // P(survive 24 roulettes) = 1e-24
 constexpr uint32_t kQueueCap = 128u;                        // entries per queued generation and warp
 constexpr uint32_t kQueueFields = 5u;                       // x, y, z, photon offset, fate word
@@ -64,14 +75,14 @@ struct WalkArgs {
     uint64_t first;                 // first global photon index of this launch; the launch must not
     uint64_t count;                 // cross a multiple of 2^32, and count <= 2^30 (the host splits)
     unsigned long long* tallies;    // global u64[2*shells]: heat_fx | heat2_fx
-    unsigned long long* counters;   // global u64[4]: events, photons, range flag, -
-    const float2* azimuth;          // global (cos, sin)(2 pi i / 1024)
+    unsigned long long* counters;   // global u64[4]: events, photons, range flag, shared-memory-map error
+    const float2* directions;       // global [256] (-ln2 cos, -ln2 sin)(theta_k) | [256] (cos, sin)(phi_k)
     const uint2* deposits;          // global (deposit, rescaled deposit^2) of event e, e = 1 .. last event of gen[n_gen-1]
     uint32_t* queues;               // global scratch: kQueueBytesPerWarp per warp of the grid (survivor queues)
     float shells_per_mfp;           // reference photon.c:9
     uint32_t shells;                // SHELLS (reference params.h:5)
     uint32_t last_bits;             // 0x4B000000 + SHELLS-1 : clamp in the magic-number domain
-    uint32_t flush_blocks;          // Philox blocks (3 events) a warp walks between drains
+    uint32_t flush_blocks;          // Philox blocks (4 events) a warp walks between drains
     uint32_t check_shift;           // a drained word >= 2^check_shift raises the range flag (31)
     uint32_t n_gen;                 // generations in `gen` (a photon surviving them all is dropped)
     GenPlan gen[kMaxGenerations];
@@ -80,12 +91,13 @@ struct WalkArgs {
 constexpr uint32_t kMagicBits = 0x4B000000u;     // float 2^23
 constexpr uint32_t kFateSurvive = 429496729u;    // floor(0.1 * 2^32): survive roulette iff fate < this
 constexpr float kLn2 = 0.693147182464599609375f;
+constexpr float kOneMinusHalfUlp = 0.999999940395355224609375f;   // 1 - 2^-24
 
 // shared-memory bytes of one block
 inline uint32_t walk_smem_bytes(uint32_t shells, bool lane_private, uint32_t block_threads)
 {
     (void)block_threads;
-    return kAzimuthBytes + (lane_private ? shells * 256u : 2u * (shells + 31u) * 4u);
+    return (kSmemTableAbs - kSmemUserBase) + kDirTableBytes + (lane_private ? shells * 256u : 2u * (shells + 31u) * 4u);
 }
 
 #ifdef __CUDACC__
@@ -109,25 +121,37 @@ __device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
     return r;
 }
+// byte SEL of `word` into byte 1 of the result, byte 0 of `low` into byte 0, zeros above: the byte
+// offset row * 256 + low of a direction-table entry in ONE instruction (PRMT)
+template <int SEL>
+__device__ __forceinline__ uint32_t row_offset(uint32_t word, uint32_t low)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(low), "n"(0x5504 | (SEL << 4)));
+    return r;
+}
+// bytes 0-1 of `word` (a shell number) into bytes 1-2, byte 0 of `low` into byte 0: shell * 256 + low
+__device__ __forceinline__ uint32_t shell_offset(uint32_t word, uint32_t low)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0x5104;" : "=r"(r) : "r"(word), "r"(low));
+    return r;
+}
+// The direction table is read-only after the block's first barrier: a pure function of the offset.
+template <uint32_t BASE>
+__device__ __forceinline__ float2 lds_f32x2(uint32_t off)
+{
+    float2 r;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(r.x), "=f"(r.y) : "r"(off), "n"(BASE));
+    return r;
+}
 // No "memory" clobber: the histograms are touched by these atomics and by drain_slice (an
 // out-of-line call) only, so the compiler stays free to hoist the next event's table look-up
 // and arithmetic above the atomics of this one.
-__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v)
+template <uint32_t BASE>
+__device__ __forceinline__ void red_shared_add(uint32_t off, uint32_t v)
 {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v));
-}
-// The azimuth table is read-only after the block's first barrier: a pure function of the address.
-__device__ __forceinline__ float2 lds_f32x2(uint32_t addr)
-{
-    float2 r;
-    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ uint32_t atom_shared_exch0(uint32_t addr)
-{
-    uint32_t r;
-    asm volatile("atom.shared.exch.b32 %0, [%1], 0;" : "=r"(r) : "r"(addr) : "memory");
-    return r;
+    asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(off), "r"(v), "n"(BASE));
 }
 __device__ __forceinline__ uint32_t lanemask_lt()
 {
@@ -188,52 +212,64 @@ __device__ __noinline__ uint32_t drain_slice(uint32_t* bins, unsigned long long*
 //         a position vector nor an azimuth.  A separately selectable cross-check ("walk_mode" = 1):
 //         NOT the path the north star names (it skips the position update and the direction
 //         resampling), never used for the headline or the roofline figure.
-template <int ROUNDS, int BLOCK, int MIN_BLOCKS, bool LANE_PRIVATE, bool RADIAL = false>
+// PPL:    photons per lane (independent dependency chains per thread); a cohort is 32 * PPL photons.
+template <int ROUNDS, int BLOCK, int MIN_BLOCKS, bool LANE_PRIVATE, bool RADIAL = false, int PPL = 2>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __grid_constant__ WalkArgs a)
 {
-    extern __shared__ __align__(16) uint32_t smem[];     // [azimuth table 8 KB | histograms]
+    extern __shared__ __align__(16) uint32_t smem[];     // [gap | direction table 64 KB | histograms]
     __shared__ uint32_t drain_ticket;
     constexpr uint32_t WARPS = BLOCK / 32;
+    constexpr uint32_t COHORT = 32u * PPL;
+    static_assert(2u * COHORT <= kQueueCap, "a survivor queue must hold two cohorts");
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t wid = tid >> 5;
+    // the table must start at kSmemTableAbs of the shared window (walk_smem_bytes() pays for the gap)
     const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-    const uint32_t bins_base = smem_base + kAzimuthBytes;
+    if (smem_base < kSmemUserBase || smem_base > kSmemTableAbs) {
+        if (tid == 0u) atomicOr(&a.counters[3], 1ull);      // reported by the host as an internal error
+        return;
+    }
+    uint32_t* const table = smem + (kSmemTableAbs - smem_base) / 4u;
+    uint32_t* const bins = table + kDirTableBytes / 4u;
     const uint32_t plain_bins = a.shells + 31u;                              // per kind, plain layout
     const uint32_t nwords = LANE_PRIVATE ? a.shells * 64u : 2u * plain_bins;
     // this warp's survivor queues: [generation 1|2][field][kQueueCap], in global memory (a few
     // accesses per cohort; L2-resident), so that shared memory holds only the table and tallies
     uint32_t* const queue = a.queues + static_cast<size_t>(blockIdx.x * WARPS + wid) * (kQueueBytesPerWarp / 4u);
 
-    {   // stage the azimuth table and clear the histograms
-        const float4* src = reinterpret_cast<const float4*>(a.azimuth);
-        float4* dst = reinterpret_cast<float4*>(smem);
-        for (uint32_t i = tid; i < kAzimuthEntries / 2; i += BLOCK) dst[i] = __ldg(src + i);
-        uint32_t* bins = smem + kAzimuthBytes / 4u;
+    {   // stage the direction table (16 copies of every entry) and clear the histograms
+        float2* dst = reinterpret_cast<float2*>(table);
+        for (uint32_t i = tid; i < kDirTableBytes / 8u; i += BLOCK)
+            dst[i] = __ldg(a.directions + (i >> 5) + ((i & 16u) ? kDirEntries : 0));
         for (uint32_t i = tid; i < nwords; i += BLOCK) bins[i] = 0u;
         if (tid == 0u) drain_ticket = 0u;
     }
     __syncthreads();
 
-    // byte address of this lane's heat slot for magic-domain shell bits sb: (sb << SHIFT) + bias
-    constexpr uint32_t SHIFT = LANE_PRIVATE ? 8u : 2u;
-    const uint32_t addr_bias = bins_base + (LANE_PRIVATE ? lane * 4u : 0u) - (kMagicBits << SHIFT);
-    const uint32_t heat2_off = LANE_PRIVATE ? 128u : plain_bins * 4u;
+    // byte offset (from kSmemBinsAbs) of this lane's heat word for magic-domain shell bits sb:
+    // lane-private: shell * 256 + lane * 4 by one PRMT; plain: (sb << 2) + bias
+    const uint32_t lane_low = lane * 4u;
+    const uint32_t plain_bias = 0u - (kMagicBits << 2);
+    const uint32_t heat2_off = plain_bins * 4u;            // plain layout; lane-private: 128
     // plain layout: lane l clamps to slot SHELLS-1+l, so the overflow bin never serialises a warp
     const uint32_t clamp_bits = LANE_PRIVATE ? a.last_bits : a.last_bits + lane;
+    // byte offsets of this lane's copies inside a direction-table row
+    const uint32_t polar_low = (lane & 15u) * 8u, azimuth_low = polar_low + 128u;
 
     // Philox round 0 with the counter folded in: c0 = first_lo + rel, c1 = first_hi, c3 = 0.
     //   M0 * c0 = M0 * rel + M0 * first_lo   (no wrap: the launch stays inside one 2^32 window)
     const uint64_t m0_first = static_cast<uint64_t>(kPhiloxM0) * static_cast<uint32_t>(a.first);
     const uint32_t c1k0 = static_cast<uint32_t>(a.first >> 32) ^ a.keys.k[0];
 
-    // two photons per lane: position (mean-free-path units, photon.c:12-14), photon offset
-    // from a.first, roulette fate word, "this slot holds a photon"
-    float2 px = make_float2(0.0f, 0.0f);    // x of both photons, packed
-    float py[2] = { 0.0f, 0.0f }, pz[2] = { 0.0f, 0.0f };
-    uint32_t rel[2], fate[2];
-    bool act[2], surv[2];
-    uint32_t r[2][4] = {};                  // the Philox block of each photon whose events are running
+    // PPL photons per lane: position (mean-free-path units, photon.c:12-14), photon offset from
+    // a.first, roulette fate word, "this slot holds a photon"
+    float px[PPL], py[PPL], pz[PPL];
+    uint32_t rel[PPL], fate[PPL];
+    bool act[PPL], surv[PPL];
+    uint32_t r[PPL][4] = {};                // the Philox block of each photon whose events are running
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) px[j] = py[j] = pz[j] = 0.0f;
 
     unsigned long long n_events = 0ull;     // warp-uniform
     uint32_t range_flag = 0u;
@@ -246,82 +282,64 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     auto drain = [&]() {
         uint32_t ticket = 0u;
         if (lane == 0u) ticket = atomicAdd(&drain_ticket, 1u);
-        range_flag |= drain_slice<BLOCK, LANE_PRIVATE>(smem + kAzimuthBytes / 4u, a.tallies, a.shells,
+        range_flag |= drain_slice<BLOCK, LANE_PRIVATE>(bins, a.tallies, a.shells,
                                                        __shfl_sync(0xffffffffu, ticket, 0) % WARPS, a.check_shift);
     };
 
-    // One scatter event (reference photon.c:21-43) of slot S of the current Philox block for
-    // both photons of the lane: spin, hop, drop.  `dep` / `dep2` are the warp-uniform deposit
-    // (1-albedo) * w and its rescaled square.
+    // One scatter event (reference photon.c:21-43) from word S of the current Philox block for
+    // every photon of the lane: spin, hop, drop.  `dep` / `dep2` are the warp-uniform deposit
+    // (1-albedo) * w and its rescaled square.  Bits of the event word v:
+    //    9..31  step:   xi = (m + 1/2) 2^-23, m = v >> 9 (midpoint rule; never 0 or 1)
+    //    8..15  polar:  cos(theta) = (2k + 1)/256 - 1, sin(theta) from the table
+    //    0..7   azimuth: phi = 2 pi k / 256, (cos, sin) from the table
+    // (the polar index shares bits 9..15 with the step, where they only decide the step's last
+    // seven mantissa bits: the step keeps a 23-bit marginal, the coupling is below 2^-16 in xi)
     auto event = [&](auto slot_tag, auto partial_tag, uint32_t dep, uint32_t dep2) {
         constexpr int S = decltype(slot_tag)::value;
         constexpr bool PARTIAL = decltype(partial_tag)::value;
-        // The two photons of the lane are one packed FP32 pair wherever both need the same
-        // operation (Blackwell FFMA2 / FMUL2 / FADD2: two results per issue slot); .x = photon 0.
-        const uint32_t v0 = r[0][S], v1 = r[1][S];
-        float2 rad;
-        if constexpr (RADIAL) {
-            // mu = cos of the angle between r and the new direction, 2 mu = (2k+1)/256 - 2 from bits 1..9
-            const float2 mu2 = __ffma2_rn(make_float2(__uint_as_float((v0 & 0x3FEu) | 0x4B000001u), __uint_as_float((v1 & 0x3FEu) | 0x4B000001u)),
-                                          make_float2(0.00390625f, 0.00390625f), make_float2(-32770.0f, -32770.0f));
-            const float2 f = make_float2(__uint_as_float(__funnelshift_r(v0, 0xFEu, 10)), __uint_as_float(__funnelshift_r(v1, 0xFEu, 10)));
-            float2 lg = __fadd2_rn(make_float2(-f.x, -f.y), make_float2(1.5f, 1.5f));
-            lg.x = mufu_lg2(lg.x);
-            lg.y = mufu_lg2(lg.y);
-            const float2 t = __ffma2_rn(lg, make_float2(-kLn2, -kLn2), make_float2(-kLn2, -kLn2));
-            // px holds the radius of both photons: r'^2 = r^2 + t^2 + (t r)(2 mu), >= 0 up to rounding
-            const float2 r2 = __ffma2_rn(__fmul2_rn(t, px), mu2, __ffma2_rn(t, t, __fmul2_rn(px, px)));
-            rad.x = mufu_sqrt(fmaxf(r2.x, 0.0f));
-            rad.y = mufu_sqrt(fmaxf(r2.y, 0.0f));
-            px = rad;
-        } else {
-        // spin: cos(theta) = (2k+1)/512 - 1 from bits 1..9 (exact), sin(theta) by MUFU.SQRT,
-        // azimuth (cos, sin) from the table, indexed by 10 bits of word 3
-        const float2 ct = __ffma2_rn(make_float2(__uint_as_float((v0 & 0x3FEu) | 0x4B000001u), __uint_as_float((v1 & 0x3FEu) | 0x4B000001u)),
-                                     make_float2(0.001953125f, 0.001953125f), make_float2(-16385.0f, -16385.0f));
-        float2 st = __ffma2_rn(make_float2(-ct.x, -ct.y), ct, make_float2(1.0f, 1.0f));
-        st.x = mufu_sqrt(st.x);
-        st.y = mufu_sqrt(st.y);
-        const uint32_t az0 = S == 0 ? (r[0][3] << 3) & 0x1FF8u : (r[0][3] >> (S == 1 ? 7 : 17)) & 0x1FF8u;
-        const uint32_t az1 = S == 0 ? (r[1][3] << 3) & 0x1FF8u : (r[1][3] >> (S == 1 ? 7 : 17)) & 0x1FF8u;
-#if TMC_EXPERIMENT == 2   /* conflict-free table address (wrong physics; timing experiment only) */
-        const float2 cs0 = lds_f32x2(smem_base + ((az0 & 0x1F00u) | (lane << 3)));
-        const float2 cs1 = lds_f32x2(smem_base + ((az1 & 0x1F00u) | (lane << 3)));
-#else
-        const float2 cs0 = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(smem) + az0);
-        const float2 cs1 = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(smem) + az1);
-#endif
-        // hop: xi = 2 * (1.5 - f), f = 1 + (v >> 10) * 2^-23; t = -ln(xi)
-        const float2 f = make_float2(__uint_as_float(__funnelshift_r(v0, 0xFEu, 10)), __uint_as_float(__funnelshift_r(v1, 0xFEu, 10)));
-        float2 lg = __fadd2_rn(make_float2(-f.x, -f.y), make_float2(1.5f, 1.5f));
-        lg.x = mufu_lg2(lg.x);
-        lg.y = mufu_lg2(lg.y);
-        const float2 t = __ffma2_rn(lg, make_float2(-kLn2, -kLn2), make_float2(-kLn2, -kLn2));
-        const float2 ts = __fmul2_rn(t, st);
-        px = __ffma2_rn(t, ct, px);
-        py[0] = fmaf(ts.x, cs0.x, py[0]);
-        pz[0] = fmaf(ts.x, cs0.y, pz[0]);
-        py[1] = fmaf(ts.y, cs1.x, py[1]);
-        pz[1] = fmaf(ts.y, cs1.y, pz[1]);
-        // drop: shell = min(trunc(|r| * shells_per_mfp), SHELLS-1) without F2I: add 2^23 with
-        // round-toward-zero, clamp the raw bits, the mantissa is the integer.
-        const float2 xx = __fmul2_rn(px, px);
-        rad.x = mufu_sqrt(fmaf(pz[0], pz[0], fmaf(py[0], py[0], xx.x)));
-        rad.y = mufu_sqrt(fmaf(pz[1], pz[1], fmaf(py[1], py[1], xx.y)));
-        }
-        const float2 sbf = __ffma2_rz(rad, make_float2(a.shells_per_mfp, a.shells_per_mfp), make_float2(8388608.0f, 8388608.0f));
-        const uint32_t sb[2] = { min(__float_as_uint(sbf.x), clamp_bits), min(__float_as_uint(sbf.y), clamp_bits) };
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const uint32_t addr = (sb[j] << SHIFT) + addr_bias;
-#if TMC_EXPERIMENT == 1   /* one atomic instead of two (timing experiment only) */
-            if (!PARTIAL || act[j]) red_shared_add(addr, dep + dep2);
-#else
-            if (!PARTIAL || act[j]) {
-                red_shared_add(addr, dep);
-                red_shared_add(addr + heat2_off, dep2);
+        for (int j = 0; j < PPL; ++j) {
+            const uint32_t v = r[j][S];
+            // hop: L = log2(xi) <= 0, step t = -ln2 * L (photon.c:21); -ln2 is folded into the polar table
+            const float f = __uint_as_float(__funnelshift_r(v, 0xFEu, 9));       // 1 + m 2^-23
+            const float L = mufu_lg2(f - kOneMinusHalfUlp);
+            const float2 pol = lds_f32x2<kSmemTableAbs>(row_offset<1>(v, polar_low));
+            float rad;
+            if constexpr (RADIAL) {
+                // px holds the radius: r'^2 = r^2 + t^2 + 2 r (t mu), >= 0 up to rounding
+                const float t = L * -kLn2, tmu = L * pol.x;
+                const float r2 = fmaf(px[j] + px[j], tmu, fmaf(t, t, px[j] * px[j]));
+                rad = mufu_sqrt(fmaxf(r2, 0.0f));
+                px[j] = rad;
+            } else {
+                // spin (photon.c:35-43, sampled directly) and move (photon.c:22-24)
+                const float2 azi = lds_f32x2<kSmemTableAbs>(row_offset<0>(v, azimuth_low));
+                const float ts = L * pol.y;
+                px[j] = fmaf(L, pol.x, px[j]);
+                py[j] = fmaf(ts, azi.x, py[j]);
+                pz[j] = fmaf(ts, azi.y, pz[j]);
+                rad = mufu_sqrt(fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j])));
             }
+            // drop: shell = min(trunc(|r| * shells_per_mfp), SHELLS-1) (photon.c:26-29) without F2I:
+            // add 2^23 with round-toward-zero, clamp the raw bits, the mantissa is the integer.
+            const uint32_t sb = min(__float_as_uint(__fmaf_rz(rad, a.shells_per_mfp, 8388608.0f)), clamp_bits);
+            if constexpr (LANE_PRIVATE) {
+                const uint32_t off = shell_offset(sb, lane_low);
+                if (!PARTIAL || act[j]) {
+#if TMC_EXPERIMENT == 1   /* one atomic instead of two (wrong tallies; timing experiment only) */
+                    red_shared_add<kSmemBinsAbs>(off, dep + dep2);
+#else
+                    red_shared_add<kSmemBinsAbs>(off, dep);
+                    red_shared_add<kSmemBinsAbs + 128u>(off, dep2);
 #endif
+                }
+            } else {
+                const uint32_t off = (sb << 2) + plain_bias;
+                if (!PARTIAL || act[j]) {
+                    red_shared_add<kSmemBinsAbs>(off, dep);
+                    red_shared_add<kSmemBinsAbs>(off + heat2_off, dep2);
+                }
+            }
         }
     };
 
@@ -330,7 +348,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
         constexpr bool PARTIAL = decltype(partial_tag)::value;
         const uint32_t ev_first = a.gen[g].first_event;
         const uint32_t ev_last = ev_first + a.gen[g].n_events - 1u;
-        const uint32_t b_first = ev_first / 3u, b_last = ev_last / 3u;
+        const uint32_t b_first = ev_first / kEventsPerBlock, b_last = ev_last / kEventsPerBlock;
         // The warp-uniform weight schedule: event e deposits (1-albedo) * w(e), rounded, and its
         // rescaled square; both come from a table the host computed with the exact integer
         // recurrence (tmc_api.cu: deposit_table), one broadcast load per event.
@@ -345,26 +363,31 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
         // draws block b+1 while the events of block b run: the Philox rounds (IMAD.WIDE on the
         // FMA-heavy pipe, LOP3) and the event arithmetic (FP32, MUFU, shared memory) use
         // different pipes and have no data dependence, so ptxas interleaves them.
-        auto draw = [&](uint32_t b, uint32_t (&out)[2][4]) {
+        auto draw = [&](uint32_t b, uint32_t (&out)[PPL][4]) {
             const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * b;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < PPL; ++j) {
                 const uint64_t p0 = mad_wide(rel[j], kPhiloxM0, m0_first);
                 philox4x32_rounds<1, ROUNDS>(a.keys, static_cast<uint32_t>(p1 >> 32) ^ c1k0, static_cast<uint32_t>(p1),
                                              static_cast<uint32_t>(p0 >> 32) ^ a.keys.k[1], static_cast<uint32_t>(p0), out[j]);
             }
         };
-        auto three_events = [&](uint32_t (&cur)[2][4]) {
+        auto take_block = [&](uint32_t (&cur)[PPL][4]) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < PPL; ++j)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) r[j][k] = cur[j][k];
+        };
+        auto four_events = [&](uint32_t (&cur)[PPL][4]) {
+            take_block(cur);
             absorb();
             event(IntTag<0>{}, partial_tag, dep, dep2);
             absorb();
             event(IntTag<1>{}, partial_tag, dep, dep2);
             absorb();
             event(IntTag<2>{}, partial_tag, dep, dep2);
+            absorb();
+            event(IntTag<3>{}, partial_tag, dep, dep2);
         };
         auto maybe_drain = [&](uint32_t blocks) {
             blocks_since_drain += blocks;
@@ -373,29 +396,27 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                 blocks_since_drain = 0u;
             }
         };
-        // first / last block of the generation (in `cur`): only slots s_lo .. s_hi belong to it
-        auto ragged_block = [&](uint32_t b, uint32_t (&cur)[2][4], uint32_t s_lo, uint32_t s_hi) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) r[j][k] = cur[j][k];
+        // first / last block of the generation (in `cur`): only words s_lo .. s_hi belong to it
+        auto ragged_block = [&](uint32_t b, uint32_t (&cur)[PPL][4], uint32_t s_lo, uint32_t s_hi) {
+            take_block(cur);
             if (g == 0u && b == 0u) {            // pseudo-event 0 of a fresh photon: its fate word
-                fate[0] = r[0][0];               // (short generations can start inside block 0 too:
-                fate[1] = r[1][0];               //  those carry their fate, already multiplied by 10)
-            }
+#pragma unroll
+                for (int j = 0; j < PPL; ++j) fate[j] = r[j][0];
+            }                                    // (later generations that start inside block 0 carry their fate)
             if (s_lo == 0u) { absorb(); event(IntTag<0>{}, partial_tag, dep, dep2); }
             if (s_lo <= 1u && s_hi >= 1u) { absorb(); event(IntTag<1>{}, partial_tag, dep, dep2); }
-            if (s_hi == 2u) { absorb(); event(IntTag<2>{}, partial_tag, dep, dep2); }
+            if (s_lo <= 2u && s_hi >= 2u) { absorb(); event(IntTag<2>{}, partial_tag, dep, dep2); }
+            if (s_hi == 3u) { absorb(); event(IntTag<3>{}, partial_tag, dep, dep2); }
             maybe_drain(1u);
         };
-        const uint32_t s_first = ev_first - 3u * b_first, s_last = ev_last - 3u * b_last;
-        uint32_t ra[2][4], rb[2][4];            // ping-pong: the block being walked / the next one
+        const uint32_t s_first = ev_first - kEventsPerBlock * b_first, s_last = ev_last - kEventsPerBlock * b_last;
+        uint32_t ra[PPL][4], rb[PPL][4];        // ping-pong: the block being walked / the next one
         draw(b_first, ra);
         if (b_first == b_last) {
             ragged_block(b_first, ra, s_first, s_last);
         } else {
             draw(b_first + 1u, rb);
-            ragged_block(b_first, ra, s_first, 2u);
+            ragged_block(b_first, ra, s_first, kEventsPerBlock - 1u);
             // full blocks b_first+1 .. b_last-1, the current one in rb.  Chunks of at most
             // flush_blocks blocks run without a call, so the Philox keys stay in uniform registers.
             uint32_t b = b_first + 1u;
@@ -404,15 +425,15 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                 const uint32_t done = chunk;
                 for (; chunk >= 2u; chunk -= 2u, b += 2u) {
                     draw(b + 1u, ra);
-                    three_events(rb);
+                    four_events(rb);
                     draw(b + 2u, rb);
-                    three_events(ra);
+                    four_events(ra);
                 }
                 if (chunk) {
                     draw(b + 1u, ra);
-                    three_events(rb);
+                    four_events(rb);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
+                    for (int j = 0; j < PPL; ++j)
 #pragma unroll
                         for (int k = 0; k < 4; ++k) rb[j][k] = ra[j][k];
                     ++b;
@@ -421,54 +442,57 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             }
             ragged_block(b_last, rb, 0u, s_last);
         }
-        uint32_t n_act = 64u;
-        if constexpr (PARTIAL) n_act = __popc(__ballot_sync(0xffffffffu, act[0])) + __popc(__ballot_sync(0xffffffffu, act[1]));
+        uint32_t n_act = COHORT;
+        if constexpr (PARTIAL) {
+            n_act = 0u;
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) n_act += __popc(__ballot_sync(0xffffffffu, act[j]));
+        }
         n_events += static_cast<unsigned long long>(n_act) * a.gen[g].n_events;
         // roulette: the fate word is a uniform 32-bit integer; surviving (probability 0.1)
         // multiplies it by 10, which is uniform again.  The x10 weight boost is in gen[g+1].
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < PPL; ++j) {
             surv[j] = (!PARTIAL || act[j]) && fate[j] < kFateSurvive;
             if (surv[j]) fate[j] *= 10u;
         }
     };
 
-    // static cohort -> warp map: warp W owns cohorts W, W + total_warps, ... of 64 photons each
+    // static cohort -> warp map: warp W owns cohorts W, W + total_warps, ... of COHORT photons each
     const uint32_t total_warps = gridDim.x * WARPS;
     const uint32_t count = static_cast<uint32_t>(a.count);
-    const uint32_t n_cohorts = (count + 63u) / 64u;
+    const uint32_t n_cohorts = (count + COHORT - 1u) / COHORT;
     uint32_t cohort = blockIdx.x * WARPS + wid;
     uint32_t nq[2] = { 0u, 0u };            // fill of this warp's generation-1 and -2 queues
 
     for (;;) {
         uint32_t g, take;
-        if (nq[1] >= 64u) { g = 2u; take = 64u; }
-        else if (nq[0] >= 64u) { g = 1u; take = 64u; }
-        else if (cohort < n_cohorts) { g = 0u; take = min(64u, count - cohort * 64u); }
+        if (nq[1] >= COHORT) { g = 2u; take = COHORT; }
+        else if (nq[0] >= COHORT) { g = 1u; take = COHORT; }
+        else if (cohort < n_cohorts) { g = 0u; take = min(COHORT, count - cohort * COHORT); }
         else if (nq[0] > 0u) { g = 1u; take = nq[0]; }
         else if (nq[1] > 0u) { g = 2u; take = nq[1]; }
         else break;
 
-        if (g == 0u) {                      // regenerate: 64 fresh photons at the origin
+        if (g == 0u) {                      // regenerate: a cohort of fresh photons at the origin
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                rel[j] = cohort * 64u + lane * 2u + j;
-                py[j] = pz[j] = 0.0f;
+            for (int j = 0; j < PPL; ++j) {
+                rel[j] = cohort * COHORT + lane * PPL + j;
+                px[j] = py[j] = pz[j] = 0.0f;
                 fate[j] = 0u;
-                act[j] = lane * 2u + j < take;
+                act[j] = lane * PPL + j < take;
             }
-            px = make_float2(0.0f, 0.0f);
             cohort += total_warps;
         } else {                            // a cohort of parked survivors of generation g
             const uint32_t* q = queue + (g - 1u) * (kQueueFields * kQueueCap);
             const uint32_t start = nq[g - 1u] - take;
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const uint32_t e = lane * 2u + j;
+            for (int j = 0; j < PPL; ++j) {
+                const uint32_t e = lane * PPL + j;
                 act[j] = e < take;
                 const uint32_t at = act[j] ? start + e : 0u;
-                (j == 0 ? px.x : px.y) = __uint_as_float(q[0u * kQueueCap + at]);
+                px[j] = __uint_as_float(q[0u * kQueueCap + at]);
                 py[j] = __uint_as_float(q[1u * kQueueCap + at]);
                 pz[j] = __uint_as_float(q[2u * kQueueCap + at]);
                 rel[j] = q[3u * kQueueCap + at];
@@ -478,7 +502,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             nq[g - 1u] = start;
         }
 
-        bool partial = take < 64u;
+        bool partial = take < COHORT;
         for (;;) {
             if (partial) phase(BoolTag<true>{}, g);
             else phase(BoolTag<false>{}, g);
@@ -486,11 +510,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             if (g + 1u <= 2u) {             // park the survivors for a later full cohort
                 uint32_t* q = queue + g * (kQueueFields * kQueueCap);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < PPL; ++j) {
                     const uint32_t m = __ballot_sync(0xffffffffu, surv[j]);
                     const uint32_t at = nq[g] + __popc(m & lanemask_lt());
                     if (surv[j]) {
-                        q[0u * kQueueCap + at] = __float_as_uint(j == 0 ? px.x : px.y);
+                        q[0u * kQueueCap + at] = __float_as_uint(px[j]);
                         q[1u * kQueueCap + at] = __float_as_uint(py[j]);
                         q[2u * kQueueCap + at] = __float_as_uint(pz[j]);
                         q[3u * kQueueCap + at] = rel[j];
@@ -502,9 +526,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                 break;
             }
             // deeper generations (1e-3 of the photons): the survivors continue in place
-            if (!__any_sync(0xffffffffu, surv[0] || surv[1])) break;
-            act[0] = surv[0];
-            act[1] = surv[1];
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) {
+                any = any || surv[j];
+                act[j] = surv[j];
+            }
+            if (!__any_sync(0xffffffffu, any)) break;
             partial = true;
             ++g;
         }
@@ -512,7 +540,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
 
     // Final drain once every warp of the block is done.
     __syncthreads();
-    range_flag |= drain_slice<BLOCK, LANE_PRIVATE>(smem + kAzimuthBytes / 4u, a.tallies, a.shells, wid, a.check_shift);
+    range_flag |= drain_slice<BLOCK, LANE_PRIVATE>(bins, a.tallies, a.shells, wid, a.check_shift);
     uint32_t fl = range_flag;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);

@@ -1,9 +1,12 @@
 #!/bin/bash
 # tools/experiments.sh — build timing-experiment variants of the library (never shipped):
-#   1 = one shared atomic per event, 2 = conflict-free azimuth look-up, 3 = 3 Philox rounds
+#   usage: tools/experiments.sh name1 "flags1" name2 "flags2" ...   ->  tiny_mc_b200/lib/exp/libtinymc_<name>.so
+#   e.g.   tools/experiments.sh ppl1 "-DTMC_PPL=1" oneatomic "-DTMC_EXPERIMENT=1"
 set -e
 mkdir -p tiny_mc_b200/lib/exp
-for e in "$@"; do
+while [ $# -ge 2 ]; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -cudart static -shared \
-       -DTMC_EXPERIMENT=$e -o tiny_mc_b200/lib/exp/libtinymc_exp$e.so tiny_mc_b200/csrc/tmc_api.cu -ldl
+       $2 -o tiny_mc_b200/lib/exp/libtinymc_$1.so tiny_mc_b200/csrc/tmc_api.cu -ldl &
+  shift 2
 done
+wait

@@ -33,6 +33,13 @@ sanitize)
 microncu)
   timeout 900 ncu --metrics sm__cycles_elapsed.avg,smsp__inst_executed.sum,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,sm__issue_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum \
       --clock-control none --csv --log-file gpurun_out/micro_ncu.csv tiny_mc_b200/bin/tmc_microbench > gpurun_out/micro_under_ncu.jsonl 2>&1; echo "microncu rc=$?" ;;
+r2a)
+  timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "replay or other_optics or independent_of_split or single_photon or run_to_run" > gpurun_out/pytest_r2a.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_r2a.log
+  timeout 600 python tools/quick_bench.py > gpurun_out/quick.jsonl 2> gpurun_out/quick.err; echo "quick rc=$?"; cat gpurun_out/quick.jsonl
+  for v in ppl1 oneatomic; do
+    TMC_LIB=tiny_mc_b200/lib/exp/libtinymc_$v.so timeout 300 python tools/quick_bench.py default:0:0 default:768:1 default:1024:1 highalbedo:0:0 finegrid:0:0 >> gpurun_out/quick_variants.jsonl 2>> gpurun_out/quick.err; echo "variant $v rc=$?"
+  done
+  cat gpurun_out/quick_variants.jsonl ;;
 quick)
   timeout 600 python tools/quick_bench.py > gpurun_out/quick.jsonl 2> gpurun_out/quick.err; echo "quick rc=$?"; cat gpurun_out/quick.jsonl ;;
 sweep)
