@@ -14,6 +14,12 @@ only — the fixtures are what travels to the GPU box and into git).
   port_xoshiro_batches_<cfg>.npz  the same batches from oracle/photon_port.c (pinned to the
                            reference bit for bit) driven by xoshiro256** instead of glibc rand():
                            the high-statistics reference, free of rand()'s lag-3/31 correlation.
+  ref_pcg_batches_<cfg>.npz  the same batches from the UNMODIFIED photon.c compiled with -Drand=pcg31
+                           (oracle/pcg31.c: PCG32 bound to the reference's rand() calls at compile time):
+                           a second sound generator under the reference's own object code.
+  *_pershell_finegrid.npz  config 5 at its native 5 um resolution: per-shell mean and batch-means
+                           variance of the mean (256 batches of 2^19 photons), all 16384 shells,
+                           from the xoshiro port and from the unmodified reference on PCG32.
   headless_asshipped.txt   stdout of the reference `headless` built exactly as its Makefile does,
                            SEED=20141017; with ref_float_tallies.json["headless"] (same seed, same
                            32768 photons) it pins the printout formatter byte for byte.
@@ -85,6 +91,25 @@ def main():
         np.savez_compressed(GOLD / f"port_xoshiro_batches_{name}.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
                             photons_per_batch=n, chunk=chunk)
         print(f"{name} (xoshiro): total/photon {heat.sum() / (nb * n):.6f}")
+        # the UNMODIFIED reference object code on a second sound generator (rand() -> PCG32 at compile time)
+        heat, heat2, _, secs, wall = orc.run_batches(name, seeds, n, chunk=chunk, impl="reference_pcg")
+        if name == "finegrid":
+            heat = heat.reshape(nb, 128, 128).sum(axis=2)
+            heat2 = heat2.reshape(nb, 128, 128).sum(axis=2)
+        np.savez_compressed(GOLD / f"ref_pcg_batches_{name}.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
+                            photons_per_batch=n, chunk=chunk)
+        print(f"{name} (unmodified reference on pcg32): total/photon {heat.sum() / (nb * n):.6f}, wall {wall:.1f} s")
+    if not only or "finegrid_pershell" in only:
+        # config 5 per 5 um shell: mean and variance of the mean from 256 batches of 2^19 photons
+        nb, n = 256, 1 << 19
+        seeds = [5000 + 11 * b for b in range(nb)]
+        for tag, kw in (("port_xoshiro", dict(impl="port", rng="xoshiro")), ("ref_pcg", dict(impl="reference_pcg"))):
+            heat, heat2, _, secs, wall = orc.run_batches("finegrid", seeds, n, chunk=256, **kw)
+            per = heat / n
+            np.savez_compressed(GOLD / f"{tag}_pershell_finegrid.npz", mean=per.mean(axis=0),
+                                var_of_mean=per.var(axis=0, ddof=1) / nb, heat2_mean=(heat2 / n).mean(axis=0),
+                                batches=nb, photons_per_batch=n, seeds=np.array(seeds))
+            print(f"finegrid per shell ({tag}): total/photon {per.sum(axis=1).mean():.6f}, wall {wall:.1f} s")
 
 
 if __name__ == "__main__":

@@ -94,11 +94,22 @@ def ref_photon_ptr(name: str) -> C.c_void_p:
     return C.cast(_ref_cache[name].photon, C.c_void_p)
 
 
+def ref_pcg_lib(name: str) -> C.CDLL:
+    """The UNMODIFIED reference photon.c compiled with -Drand=pcg31 (oracle/Makefile, oracle/pcg31.c)."""
+    key = "pcg_" + name
+    if key not in _ref_cache:
+        l = C.CDLL(str(REF_DIR / f"libphoton_pcg_{name}.so"))
+        l.pcg31_seed.argtypes = [C.c_uint64]
+        _ref_cache[key] = l
+    return _ref_cache[key]
+
+
 RNG_KINDS = {"libc": 0, "xoshiro": 1}
 
 
 def run_batch(cfg, seed: int, n_photons: int, chunk: int = 256, impl: str = "port", ref_name: str = None, rng: str = "libc"):
-    """One srand(seed) batch.  impl: "reference" (oracle/_ref object code, libc rand() only) or
+    """One srand(seed) batch.  impl: "reference" (oracle/_ref object code, libc rand() only),
+    "reference_pcg" (the same unmodified source with rand() bound to PCG32 at compile time) or
     "port" (photon_port.c; rng "libc" = the reference's stream, "xoshiro" = a sound generator).  Returns dict(heat, heat2 [float64], heat_f, heat2_f [float32 when chunk==0], events)."""
     o = optics(cfg)
     heat = np.zeros(o.shells)
@@ -108,6 +119,10 @@ def run_batch(cfg, seed: int, n_photons: int, chunk: int = 256, impl: str = "por
     fn = None
     if impl == "reference":
         fn = ref_photon_ptr(ref_name or (cfg if isinstance(cfg, str) else "default"))
+    elif impl == "reference_pcg":
+        l = ref_pcg_lib(ref_name or (cfg if isinstance(cfg, str) else "default"))
+        l.pcg31_seed(seed)
+        fn = C.cast(l.photon, C.c_void_p)
     t0 = time.perf_counter()
     ev = lib().orc_run_batch(C.byref(o), fn, RNG_KINDS[rng], seed, n_photons, chunk, heat.ctypes.data, heat2.ctypes.data,
                              heat_f.ctypes.data, heat2_f.ctypes.data)

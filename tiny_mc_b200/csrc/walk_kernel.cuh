@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
         for (int j = 0; j < PPL; ++j) {
             const uint32_t v = r[j][S];
             // hop: L = log2(xi) <= 0, step t = -ln2 * L (photon.c:21); -ln2 is folded into the polar table
-            const float f = __uint_as_float(__funnelshift_r(v, 0xFEu, 9));       // 1 + m 2^-23
+            const float f = __uint_as_float(__funnelshift_r(v, 0x7Fu, 9));       // 0x3F800000 | m: 1 + m 2^-23
             const float L = mufu_lg2(f - kOneMinusHalfUlp);
             const float2 pol = lds_f32x2<kSmemTableAbs>(row_offset<1>(v, polar_low));
             float rad;
