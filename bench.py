@@ -7,16 +7,19 @@
 A "step" is one pass of the hot path (reference tiny_mc.c:47-49, i.e. PHOTONS calls of photon())
 over one batch of photons:
   N = 1 : BASELINE.json configs[1] — default optics, 2^26 photons per step on one GPU;
-  N > 1 : 2^29 photons per GPU per step (weak scaling; N = 8 is exactly configs[2]: 2^32 photons
-          sharded over 8 GPUs), one NCCL all-reduce of the 2*SHELLS+4 u64 tally words per step.
+  N > 1 : BASELINE.json configs[2] — 2^32 photons per step sharded over the N GPUs (the same job at
+          N = 2, 4, 8), one NCCL all-reduce of the 2*SHELLS+4 u64 tally words per step.
 There is no input data: the "inputs" are the photon index range and the seed, so nothing has
 to be resident in HBM and nothing is copied host->device; every step simulates a NEW photon range.
 
   value : device-resident — tmc_photons_device() into a device tally buffer on torch's current
           stream, CUDA events on that stream, max over ranks.
-  e2e   : the reference-facing C-ABI call tmc_photons() with HOST float tallies (kernel + D2H of
-          the tally words + float accumulation on the host), wall clock (N = 1: the library drives
-          the GPU itself; N > 1: device call + all-reduce + D2H per step).
+  e2e   : the reference-facing C-ABI call tmc_photons() with HOST float tallies, wall clock: ONE
+          process drives all N GPUs (tmc_init(N): library streams, in-library ncclReduce, D2H of
+          the tally words, float accumulation) — the path the C host program takes.  Under
+          torchrun rank 0 runs it while the other ranks wait on the host (gloo barrier).
+  checks.tally_hash : the tally words of one fixed photon range, sharded over the N GPUs —
+          the same hash at every N (and through both host paths) is the bit-reproducibility proof.
   --impl reference : the UNMODIFIED reference photon() (oracle/_ref, compiled from
           /root/reference/photon.c) on all host cores as independent processes (libc rand() is
           process-global; the repo's variant has no OpenMP), bounded sample per step.
@@ -42,7 +45,6 @@ sys.path.insert(0, str(ROOT))
 METRIC = "photons/s"
 CANONICAL_SLOTS_PER_EVENT = 88.0   # walk 35 + canonical Philox4x32-10 53
 WALK_SLOTS_PER_EVENT = 35.0        # RNG-free lower bound
-MUFU_PER_EVENT_CANONICAL = 3.0     # lg2, sqrt, sqrt (simplified Marsaglia)
 LANES_PER_CLK_PER_SM = 128.0
 MUFU_PER_CLK_PER_SM = 16.0
 
@@ -169,12 +171,39 @@ def emit(line: dict):
 
 
 # ------------------------------------------------------------------------------ our arm
+NAMED = {   # photons per step: (one GPU, whole job on N > 1 GPUs) and the BASELINE.json config each is
+    "default": ((1 << 26, "BASELINE configs[1]"), (1 << 32, "BASELINE configs[2]")),
+    # 2^22 photons = 3e10 events per step on one GPU: ~28 cohorts per warp, so the one-cohort tail is ~1 %
+    "highalbedo": ((1 << 22, "BASELINE configs[3] optics, 2^22-photon steps"), (1 << 26, "BASELINE configs[3] optics, 2^26-photon steps")),
+    "finegrid": ((1 << 26, "BASELINE configs[4] optics, 2^26-photon steps"), (1 << 30, "BASELINE configs[4]")),
+}
+HASH_SEED, HASH_PHOTONS = 0x5EED, 1 << 26      # the fixed range behind checks.tally_hash at every N
+
+
+def fnv64(words) -> str:
+    """FNV-1a (64 bit) over the little-endian bytes of the u64 tally words."""
+    h = 0xCBF29CE484222325
+    for b in words.astype("<u8").tobytes():
+        h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+def ncu_facts(config: str):
+    """Per-event instruction counts of the shipped kernel from the committed ncu capture (tools/ncu_facts.py)."""
+    path = ROOT / "profiles" / "r02_ncu_facts.json"
+    try:
+        return json.loads(path.read_text()).get(config)
+    except (OSError, ValueError):
+        return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import tiny_mc_b200 as tmc
+    from tiny_mc_b200.shards import shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -186,29 +215,35 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; tiny_mc_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")     # host-side waits that keep every GPU idle
 
     cfg = tmc.CONFIGS[args.config]
     shells = cfg["shells"]
-    per_gpu = args.photons_per_gpu or ((1 << 26) if world == 1 else (1 << 29))
-    if args.config == "highalbedo" and not args.photons_per_gpu:
-        per_gpu >>= 4    # 2^22 photons = 3e10 events per step: ~28 cohorts per warp, so the one-cohort tail is ~1 %
-    per_step = per_gpu * world
+    per_step, named = NAMED[args.config][0 if world == 1 else 1]
+    if args.photons_per_gpu:
+        per_step, named = args.photons_per_gpu * world, "custom size"
+    per_gpu = per_step // world
     seed = 0x5EED
     tmc.set_option("philox_rounds", args.philox_rounds)
     words = 2 * shells + 4
     tallies = torch.zeros(words, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    launches = 0
 
-    from tiny_mc_b200.shards import shard_range
-
-    def device_step(step: int):
-        first, count = shard_range(step * per_step, per_step, rank, world)    # this rank's photon indices
+    def device_walk(first_photon: int, n_photons: int):
+        nonlocal launches
+        first, count = shard_range(first_photon, n_photons, rank, world)    # this rank's photon indices
         tmc.photons_device(args.config, seed, first, count, local_rank, tallies.data_ptr(), stream.cuda_stream)
+        launches += tmc.last_run_info().gpu_launches
         if world > 1:
             dist.all_reduce(tallies)     # the single collective: 2*SHELLS+4 int64 words, exact
+
+    def device_step(step: int):
+        device_walk(step * per_step, per_step)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -225,10 +260,10 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     tallies.zero_()
-    total_tally_check = 0
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     sync_all()
+    launches = 0
     wall0 = time.perf_counter()
     for k in range(args.steps):
         flush_buf.fill_(k & 0xFF)       # L2 flush between timed iterations (outside the events)
@@ -239,116 +274,123 @@ def run_ours(args):
         stops[k].record(stream)
     sync_all()
     wall = time.perf_counter() - wall0
+    timed_launches = launches
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, float(timed_launches)], dtype=torch.float64, device=dev)
     if world > 1:
+        tl = t.clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    # the same loop with Philox4x32-7 (the smallest Crush-resistant variant of Salmon et al.), reported beside the headline
-    philox7_value = None
-    if args.philox_rounds == 10 and world == 1:
-        tmc.set_option("philox_rounds", 7)
-        for w in range(args.warmup):
-            device_step(w)
-        s7 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        torch.cuda.synchronize()
-        s7[0].record(stream)
-        for k in range(args.steps):
-            device_step(args.warmup + k)
-        s7[1].record(stream)
-        torch.cuda.synchronize()
-        philox7_value = per_step * args.steps / (s7[0].elapsed_time(s7[1]) * 1e-3)
-        tmc.set_option("philox_rounds", 10)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        timed_launches = int(tl[1].item())
+    dev_ms = float(t[0].item())
     clocks = sampler.stop() if rank == 0 else None
+    tmc.device_tallies_check(args.config, local_rank, tallies.data_ptr(), stream.cuda_stream)   # mandatory after photons_device
     host_tallies = tallies.cpu().numpy().astype(np.uint64)
     events_last = int(host_tallies[2 * shells])
     flag = int(host_tallies[2 * shells + 2])
     photons_counted = int(host_tallies[2 * shells + 1])
-    if world == 1:
-        events_per_photon = events_last / max(photons_counted, 1)
-    else:
-        events_per_photon = events_last / max(photons_counted, 1)
+    events_per_photon = events_last / max(photons_counted, 1)
     value = per_step * args.steps / (dev_ms * 1e-3)
 
-    # ---- end to end through the reference-facing C-ABI call with HOST tallies ("e2e") ----
+    # ---- the same fixed photon range at every N: its tally words must hash the same (north star:
+    #      "bit-reproducible across 1/2/4/8 GPUs"; reference loop tiny_mc.c:47-49 sharded) ----
+    saved_seed, seed = seed, HASH_SEED
+    tallies.zero_()
+    device_walk(0, HASH_PHOTONS)
+    torch.cuda.synchronize()
+    seed = saved_seed
+    hash_words = tallies.cpu().numpy().astype(np.uint64)[: 2 * shells]
+    tally_hash = fnv64(hash_words)
+
+    # ---- end to end through the reference-facing C-ABI call with HOST tallies ("e2e"): ONE process drives
+    #      all N GPUs through tmc_init(N) + tmc_photons() (library streams, in-library NCCL reduce, D2H,
+    #      float accumulation); under torchrun rank 0 does it while the other ranks wait on the host ----
     heat = np.zeros(shells, np.float32)
     heat2 = np.zeros(shells, np.float32)
     d2h = words * 8
-    if world == 1:
-        tmc.init(1)
+    e2e_value = lib_hash = info = absorbed = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+    if rank == 0:
+        tmc.init(world)
+        tmc.prepare(args.config)
         for w in range(args.warmup):
-            tmc.photons(args.config, seed, w * per_step, per_gpu, heat, heat2)
+            tmc.photons(args.config, seed, w * per_step, per_step, heat, heat2)
         heat[:] = 0
         heat2[:] = 0
-        torch.cuda.synchronize()
         e0 = time.perf_counter()
         for k in range(args.steps):
-            tmc.photons(args.config, seed, (args.warmup + k) * per_step, per_gpu, heat, heat2)
+            tmc.photons(args.config, seed, (args.warmup + k) * per_step, per_step, heat, heat2)
         e2e_s = time.perf_counter() - e0
         info = tmc.last_run_info().as_dict()
-        absorbed = float(heat.sum()) / (per_gpu * args.steps)
-    else:
-        pinned = torch.empty(words, dtype=torch.int64).pin_memory()
-        sync_all()
-        e0 = time.perf_counter()
-        for k in range(args.steps):
-            tallies.zero_()
-            device_step(args.warmup + k)
-            pinned.copy_(tallies, non_blocking=False)       # D2H of the reduced tally words
-            fx = pinned.numpy().astype(np.uint64)
-            tmc.fx_accumulate(args.config, fx[:shells].copy(), fx[shells:2 * shells].copy(), heat, heat2)
-        sync_all()
-        e2e_s = time.perf_counter() - e0
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
-        info = tmc.last_run_info().as_dict()
-        absorbed = float(heat.sum()) / (per_step * args.steps)
-    e2e_value = per_step * args.steps / e2e_s
+        absorbed = float(heat.astype(np.float64).sum()) / (per_step * args.steps)
+        e2e_value = per_step * args.steps / e2e_s
+        hfx, h2fx = tmc.photons_fx(args.config, HASH_SEED, 0, HASH_PHOTONS)
+        lib_hash = fnv64(np.concatenate([hfx, h2fx]))
+        tmc.finalize()
+    if world > 1:
+        dist.barrier(group=cpu_group)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline: issue slots (FP32/INT) and MUFU, SURVEY §8(d) ----
+    # ---- roofline: issue slots of the SM sub-partitions (FP32/INT/MUFU all issue through them), SURVEY §8(d) ----
     f_sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     events_per_s_per_gpu = value / world * events_per_photon
     issue_peak = sms * LANES_PER_CLK_PER_SM * f_sm_hz
     mufu_peak = sms * MUFU_PER_CLK_PER_SM * f_sm_hz
-    achieved = events_per_s_per_gpu * CANONICAL_SLOTS_PER_EVENT
+    facts = ncu_facts(args.config)
     roofline = {
         "bound": "issue",
-        "achieved": achieved / 1e12, "peak": issue_peak / 1e12, "unit": "T lane-instr/s",
-        "frac": achieved / issue_peak,
-        "traffic": 79104,   # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu capture profiles/r01_v5_default_ncu.md
-        "definition": "events/s/GPU x 88 canonical issue slots per event (SURVEY 8d: walk 35 + Philox4x32-10 53) "
-                      "/ (SMs x 128 lanes/clk x SM clock sampled during the run)",
-        "frac_walk_only_35_slots": events_per_s_per_gpu * WALK_SLOTS_PER_EVENT / issue_peak,
-        "frac_mufu_3_per_event": events_per_s_per_gpu * MUFU_PER_EVENT_CANONICAL / mufu_peak,
-        "events_per_s_per_gpu": events_per_s_per_gpu,
-        "events_per_photon": events_per_photon,
+        "unit": "T lane-instr/s",
+        "peak": issue_peak / 1e12,
         "peak_source": f"{sms} SMs x 128 lanes/clk x {f_sm_hz / 1e6:.0f} MHz (nvidia-smi median under load); "
                        "MEASURED_PEAKS.json holds HBM and bf16 peaks only - the issue rate was measured on the box: "
                        "127.4 lanes/clk/SM sustained (profiles/r01_microbench_pipes.md)",
-        "hardware_truth": "ncu of this kernel (profiles/): warp instructions per event, issue-slot, FMA-heavy, ALU, XU and "
-                          "shared-pipe utilisation; frac > 1 means fewer instructions than the canonical 88-slot budget",
-        "philox10_ceiling_events_per_s": sms * 4 * f_sm_hz / 80.0 * 32 * 3,
-        "frac_of_philox10_ceiling": events_per_s_per_gpu / (sms * 4 * f_sm_hz / 80.0 * 32 * 3),
-        "bytes_note": "HBM traffic is ~80 KB per launch (ncu dram__bytes): the kernel reads no input",
+        "events_per_s_per_gpu": events_per_s_per_gpu,
+        "events_per_photon": events_per_photon,
+        "frac_canonical_88": events_per_s_per_gpu * CANONICAL_SLOTS_PER_EVENT / issue_peak,
+        "frac_walk_only_35_slots": events_per_s_per_gpu * WALK_SLOTS_PER_EVENT / issue_peak,
+        "frac_mufu_2_per_event": events_per_s_per_gpu * 2.0 / mufu_peak,
     }
+    if facts:
+        ncu_events_per_s = facts["events"] / (facts["duration_ms"] * 1e-3)
+        roofline.update({
+            "achieved": events_per_s_per_gpu * facts["warp_instr_per_event"] / 1e12,
+            "frac": events_per_s_per_gpu * facts["warp_instr_per_event"] / issue_peak,
+            "definition": "live events/s/GPU x warp instructions per event EXECUTED by this kernel (ncu smsp__inst_executed of the "
+                          "committed capture, lane-normalised) / (SMs x 128 lanes/clk x SM clock sampled during the run) "
+                          "= the hardware issue-slot utilisation (ncu sm__issue_active of the capture: "
+                          f"{facts['issue_active_pct']:.1f} %)",
+            "warp_instr_per_event": facts["warp_instr_per_event"],
+            "frac_dispatch": (events_per_s_per_gpu * facts["dispatch_slots_per_event"] / issue_peak) if facts.get("dispatch_slots_per_event") else None,
+            "frac_fma_heavy": facts["fma_heavy_pct"] / 100.0 * events_per_s_per_gpu / ncu_events_per_s,
+            "frac_shared_pipe": facts["shared_pipe_pct"] / 100.0 * events_per_s_per_gpu / ncu_events_per_s,
+            "traffic": facts["dram_bytes"],
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full): the path reads no input, HBM is idle",
+            "ncu_capture": {"file": "profiles/r02_ncu_facts.json", "report": facts["report"], "block_threads": facts["block_threads"],
+                            "matches_this_run": facts["block_threads"] == info["threads_per_block"]},
+        })
+    else:
+        roofline.update({"achieved": None, "frac": None, "traffic": None,
+                         "definition": "no committed ncu capture for this configuration (profiles/r02_ncu_facts.json)"})
 
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+        "vs_baseline": None,
         "dtype": "f32+u32 (fp32 walk, 32-bit fixed-point weights, u64 tallies)", "data": "synthetic",
         "config": {
             "workload": (f"{args.config} optics (SHELLS={shells}, MU_A={cfg['mu_a']}, MU_S={cfg['mu_s']}, "
-                         f"{cfg['microns_per_shell']} um shells), {per_gpu} photons per GPU per step, "
-                         f"{per_step} photons per step" + (" = BASELINE configs[1]" if world == 1 and per_gpu == 1 << 26 else "")
-                         + (" = BASELINE configs[2]" if per_step == 1 << 32 else "")),
+                         f"{cfg['microns_per_shell']} um shells), {per_step} photons per step = {named}, "
+                         f"{per_gpu} photons per GPU per step"),
             "parallelism": f"photon-index shards x{world}" + (", one NCCL all-reduce of the tally words per step" if world > 1 else ""),
+            "scaling_note": "N = 1 is configs[1] (2^26 photons); N = 2, 4, 8 all run configs[2] (2^32 photons in total, "
+                            "strong scaling between them)",
             "philox_rounds": args.philox_rounds,
             "l2": "flushed between timed steps (256 MB fill); the kernel has no input to cache",
             "blocks": info["blocks_per_gpu"], "threads_per_block": info["threads_per_block"],
@@ -356,12 +398,16 @@ def run_ours(args):
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
-                "note": "C-ABI tmc_photons() with host float tallies; no inputs exist to copy host->device "
-                        "(launch arguments only); D2H = 2*SHELLS+4 u64 tally words"},
-        "gpu_launches": args.steps * world,
+                "note": f"one process, tmc_init({world}) + C-ABI tmc_photons() with HOST float tallies per step: launches on "
+                        f"{world} GPU(s)" + (", in-library ncclReduce," if world > 1 else ",") + " D2H of 2*SHELLS+4 u64 tally words, "
+                        "float accumulation; wall clock.  No inputs exist to copy host->device (launch arguments only)",
+                "library_kernel_ms_last_step": info["kernel_ms"], "library_call_ms_last_step": info["call_ms"]},
+        "gpu_launches": timed_launches,
         "roofline": roofline,
-        "philox7": {"value": philox7_value, "unit": METRIC, "note": "same workload with philox_rounds=7; the headline uses Philox4x32-10"},
-        "checks": {"absorbed_weight_per_photon": absorbed, "tally_range_flag": flag, "wall_ms_per_step": 1e3 * wall / args.steps},
+        "checks": {"absorbed_weight_per_photon": absorbed, "tally_range_flag": flag, "wall_ms_per_step": 1e3 * wall / args.steps,
+                   "tally_hash": tally_hash, "tally_hash_library_path": lib_hash,
+                   "tally_hash_of": f"FNV-1a-64 of heat_fx|heat2_fx (2*SHELLS u64 words), seed {HASH_SEED:#x}, photons [0, 2^26), "
+                                    f"sharded over {world} GPU(s): identical at every N"},
     }
     if world == 1 and not args.no_cpu_baseline:
         per_core = args.cpu_photons_per_core or ((1 << 18) if args.config != "highalbedo" else (1 << 11))

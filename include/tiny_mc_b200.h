@@ -109,6 +109,16 @@ int tmc_photons(const tmc_params* p, uint64_t seed, uint64_t first_photon, uint6
 int tmc_photons_fx(const tmc_params* p, uint64_t seed, uint64_t first_photon, uint64_t n_photons,
                    uint64_t* heat_fx, uint64_t* heat2_fx);
 
+/* n_batches consecutive sub-ranges of [first_photon, first_photon + n_photons) in ONE pass, batch b
+ * (photons first + b*n/n_batches ..., the remainder spread over the first batches) ADDED into
+ * heat_fx[b*SHELLS .. ] / heat2_fx[b*SHELLS ..]: the batch-means form of the driver loop
+ * (reference tiny_mc.c:47-49), for a standard error the reference's per-event Error column
+ * (tiny_mc.c:64) cannot give.  Every batch is sharded over all GPUs, all kernels are enqueued back
+ * to back, one reduce and one copy bring all batches home.  The sum over b is bit-identical to
+ * tmc_photons_fx of the whole range.  1 <= n_batches <= 4096.                                   */
+int tmc_photons_fx_batches(const tmc_params* p, uint64_t seed, uint64_t first_photon, uint64_t n_photons,
+                           uint32_t n_batches, uint64_t* heat_fx, uint64_t* heat2_fx);
+
 /* Device-resident, asynchronous form for one-process-per-GPU hosts (e.g. torchrun ranks):
  * enqueue the walk on `cuda_stream` (a cudaStream_t, NULL = default stream) of CUDA device
  * `device`, ADDING into the DEVICE buffer d_tallies = uint64_t[2*SHELLS + 4] laid out as
@@ -117,9 +127,19 @@ int tmc_photons_fx(const tmc_params* p, uint64_t seed, uint64_t first_photon, ui
  *   [2*SHELLS + 0..3]      events, photons, tally-range flag (non-zero = invalid), reserved
  * which the caller zeroes once.  No synchronisation and no collective: the caller sums that
  * one buffer across ranks itself (a single NCCL all-reduce of 2*SHELLS+4 int64 words).
- * Works without tmc_init.                                                                   */
+ * Works without tmc_init.
+ * MANDATORY before the tallies are used: word 2*SHELLS+2 (summed over ranks) must be 0.  The
+ * privatised u32 tallies are drained at an interval that provably cannot wrap for SHELLS <= 512
+ * and that rests on a 4x statistical margin plus a 2^31 tripwire for larger grids; this entry
+ * point cannot repeat a range by itself the way tmc_photons* do, it only raises that word.
+ * tmc_device_tallies_check() does the test for hosts that do not read the buffer themselves.  */
 int tmc_photons_device(const tmc_params* p, uint64_t seed, uint64_t first_photon, uint64_t n_photons,
                        int device, void* d_tallies, void* cuda_stream);
+
+/* Synchronise `cuda_stream`, read the four counter words of the device buffer d_tallies and return
+ * TMC_OK, or TMC_ERR_TALLY_RANGE when the range flag is set (the tallies of this buffer must then be
+ * discarded: zero it and repeat with tmc_set_option("flush_iters", smaller)).                    */
+int tmc_device_tallies_check(const tmc_params* p, int device, const void* d_tallies, void* cuda_stream);
 
 /* Fixed-point scales used for `p` (a pure function of the optics). */
 int tmc_fx_scales(const tmc_params* p, tmc_scales* out);

@@ -57,6 +57,10 @@ def main():
     r = orc.run_batch("default", HEADLESS_SEED, 32768, chunk=0, impl="reference")
     exact["headless"] = dict(config=orc.CONFIGS["default"], seed=HEADLESS_SEED, photons=32768,
                              heat_bits=bits(r["heat_f"]), heat2_bits=bits(r["heat2_f"]))
+    # the unmodified reference with rand() bound to PCG32: pins pcg31.c and the port's third generator
+    r = orc.run_batch("default", 2718, 4096, chunk=0, impl="reference_pcg")
+    exact["default_pcg"] = dict(config=orc.CONFIGS["default"], seed=2718, photons=4096, rng="pcg",
+                                heat_bits=bits(r["heat_f"]), heat2_bits=bits(r["heat2_f"]))
     (GOLD / "ref_float_tallies.json").write_text(json.dumps(exact))
 
     out = subprocess.run([str(orc.REF_DIR / "headless_asshipped")], capture_output=True, text=True, check=True).stdout

@@ -33,7 +33,7 @@ typedef void (*orc_photon_fn)(float* heats, float* heats_squared);
 uint32_t orc_photon(const orc_optics* o, float* heats, float* heats_squared);
 
 /* Seed the uniform source used by orc_photon (photon_port.c explains why there are two). */
-enum { ORC_RNG_LIBC = 0, ORC_RNG_XOSHIRO = 1 };
+enum { ORC_RNG_LIBC = 0, ORC_RNG_XOSHIRO = 1, ORC_RNG_PCG = 2 };
 void orc_seed(int kind, unsigned seed);
 
 /* Per-photon event counter of the last orc_run_* call (sum over photons). */
@@ -86,6 +86,12 @@ uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_
 /* mode 0 = the 3-D walk (orc_replay), 1 = the product's reduced radial cross-check walk. */
 uint64_t orc_replay_mode(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n, int mode,
                          uint64_t* heat_fx, uint64_t* heat2_fx);
+
+/* The 3-D replay that also accumulates per_photon_sq[s] += X_s^2, X_s = one photon's total deposit in shell s
+ * (weight units): the per-PHOTON second moment behind a correct standard error of heat[s] (tiny_mc.c:64 means it,
+ * photon.c:31 accumulates per EVENT instead). */
+uint64_t orc_replay_per_photon(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n,
+                               uint64_t* heat_fx, uint64_t* heat2_fx, double* per_photon_sq);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,9 @@
  *                   is the additive-feedback generator r[i] = r[i-3] + r[i-31]; its 3-point
  *                   correlation measurably biases THIS walk (inner shells -0.3 %, outer shells
  *                   +1.5 %, > 6 sigma at 4e6 photons; DESIGN.md §7, tests/test_oracle_pinned.py).
- *                   The walk code below is byte-identical for both sources. */
+ * ORC_RNG_PCG     : PCG32 >> 1 (pcg31.c), the generator oracle/_ref/libphoton_pcg_*.so binds the
+ *                   UNMODIFIED photon.c to: port on PCG == reference on PCG, bit for bit.
+ *                   The walk code below is byte-identical for all sources. */
 static uint64_t xo[4];
 static inline uint64_t rotl64(uint64_t v, int k) { return (v << k) | (v >> (64 - k)); }
 static int xoshiro31(void)
@@ -37,6 +39,8 @@ static int xoshiro31(void)
     xo[3] = rotl64(xo[3], 45);
     return (int)(out >> 33);
 }
+int pcg31(void);               /* pcg31.c: the generator the unmodified reference is ALSO compiled against */
+void pcg31_seed(uint64_t seed);
 static int (*draw31)(void) = rand;
 
 void orc_seed(int kind, unsigned seed)
@@ -51,6 +55,9 @@ void orc_seed(int kind, unsigned seed)
             xo[i] = v ^ (v >> 31);
         }
         draw31 = xoshiro31;
+    } else if (kind == ORC_RNG_PCG) {
+        pcg31_seed(seed);
+        draw31 = pcg31;
     } else {
         srand(seed); /* tiny_mc.c:43 */
         draw31 = rand;

@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
         l.orc_replay.argtypes = [C.POINTER(Optics), C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         l.orc_replay_mode.restype = C.c_uint64
         l.orc_replay_mode.argtypes = [C.POINTER(Optics), C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        l.orc_replay_per_photon.restype = C.c_uint64
+        l.orc_replay_per_photon.argtypes = [C.POINTER(Optics), C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         l.orc_step_of_word.restype = C.c_float
         l.orc_step_of_word.argtypes = [C.c_uint32]
         l.orc_xi_of_word.restype = C.c_double
@@ -104,7 +106,7 @@ def ref_pcg_lib(name: str) -> C.CDLL:
     return _ref_cache[key]
 
 
-RNG_KINDS = {"libc": 0, "xoshiro": 1}
+RNG_KINDS = {"libc": 0, "xoshiro": 1, "pcg": 2}
 
 
 def run_batch(cfg, seed: int, n_photons: int, chunk: int = 256, impl: str = "port", ref_name: str = None, rng: str = "libc"):
@@ -178,6 +180,17 @@ def replay(cfg, seed: int, first: int, n: int, rounds: int = 10, mode: int = 0):
     heat2 = np.zeros(o.shells, np.uint64)
     ev = lib().orc_replay_mode(C.byref(o), rounds, seed, first, n, mode, heat.ctypes.data, heat2.ctypes.data)
     return heat, heat2, int(ev)
+
+
+def replay_per_photon(cfg, seed: int, first: int, n: int, rounds: int = 10):
+    """Replay with the per-PHOTON second moment: returns (heat, per_photon_sq) in weight units (float64[shells]);
+    Var(mean heat[s]) = (per_photon_sq[s] / n - (heat[s] / n)^2) / n."""
+    o = optics(cfg)
+    heat = np.zeros(o.shells, np.uint64)
+    heat2 = np.zeros(o.shells, np.uint64)
+    sq = np.zeros(o.shells, np.float64)
+    lib().orc_replay_per_photon(C.byref(o), rounds, seed, first, n, heat.ctypes.data, heat2.ctypes.data, sq.ctypes.data)
+    return fx_to_float64(cfg, heat, heat2)[0], sq
 
 
 def generation_plan(cfg, max_gen: int = 8):

@@ -33,6 +33,7 @@
 #include "oracle.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 /* Philox4x32 (Salmon et al., SC'11): multipliers and Weyl key increments. */
@@ -163,8 +164,27 @@ uint64_t orc_replay(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_
 /* mode 0: the 3-D walk; mode 1: the product's reduced radial cross-check walk ("walk_mode" = 1):
  * r'^2 = r^2 + t^2 + (t r)(2 mu), mu = cos between r and the new direction, uniform on [-1, 1]
  * because scattering is isotropic (photon.c:35-43) — same step, same mu bits, no azimuth. */
+static uint64_t replay_core(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n, int mode,
+                            uint64_t* heat_fx, uint64_t* heat2_fx, double* per_photon_sq);
+
 uint64_t orc_replay_mode(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n, int mode,
                          uint64_t* heat_fx, uint64_t* heat2_fx)
+{
+    return replay_core(o, rounds, seed, first, n, mode, heat_fx, heat2_fx, 0);
+}
+
+/* The estimator the reference's Error column means but does not compute (tiny_mc.c:64 squares per EVENT,
+ * photon.c:31): per_photon_sq[s] += X_s^2 for every photon, X_s = the photon's TOTAL deposit in shell s
+ * (weight units).  Var(mean heat[s]) = (sum X_s^2 / N - mean^2) / N.  Checks the batch-means standard
+ * error the product reports (TMC_JSON, tmc_photons_fx_batches). */
+uint64_t orc_replay_per_photon(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n,
+                               uint64_t* heat_fx, uint64_t* heat2_fx, double* per_photon_sq)
+{
+    return replay_core(o, rounds, seed, first, n, 0, heat_fx, heat2_fx, per_photon_sq);
+}
+
+static uint64_t replay_core(const orc_optics* o, uint32_t rounds, uint64_t seed, uint64_t first, uint64_t n, int mode,
+                            uint64_t* heat_fx, uint64_t* heat2_fx, double* per_photon_sq)
 {
     orc_fx_scales s;
     orc_fx_plan(o, &s);
@@ -190,9 +210,14 @@ uint64_t orc_replay_mode(const orc_optics* o, uint32_t rounds, uint64_t seed, ui
         dir_ready = 1;
     }
     uint64_t events = 0;
+    /* per-photon shell sums (only when per_photon_sq is asked for): own[s] and the list of touched shells */
+    uint64_t* own = per_photon_sq ? calloc(o->shells, sizeof(uint64_t)) : 0;
+    uint32_t* touched = per_photon_sq ? malloc(o->shells * sizeof(uint32_t)) : 0;
+    const double unit = 1.0 / (double)s.weight_one;
 
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t p = first + i;
+        uint32_t n_touched = 0;
         float x = 0.0f, y = 0.0f, z = 0.0f;   /* photon.c:12-14 */
         uint32_t w = s.weight_one;            /* photon.c:18    */
         uint32_t r[4] = { 0, 0, 0, 0 };
@@ -235,6 +260,10 @@ uint64_t orc_replay_mode(const orc_optics* o, uint32_t rounds, uint64_t seed, ui
             w -= dep;
             heat_fx[shell] += dep;
             heat2_fx[shell] += ((uint64_t)dep * dep + half) >> s.heat2_rshift;
+            if (own) {
+                if (own[shell] == 0 && dep != 0) touched[n_touched++] = shell;
+                own[shell] += dep;
+            }
             /* roulette (photon.c:45-49) */
             if (w < s.roulette_thr) {
                 if (fate >= FATE_SURVIVE)
@@ -243,6 +272,13 @@ uint64_t orc_replay_mode(const orc_optics* o, uint32_t rounds, uint64_t seed, ui
                 w *= 10u;
             }
         }
+        for (uint32_t k = 0; k < n_touched; ++k) {
+            const double x = (double)own[touched[k]] * unit;
+            per_photon_sq[touched[k]] += x * x;
+            own[touched[k]] = 0;
+        }
     }
+    free(own);
+    free(touched);
     return events;
 }

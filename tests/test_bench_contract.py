@@ -49,5 +49,13 @@ def test_gpu_arm_prints_the_contract_keys():
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in r, key
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.0 < r["frac_walk_only_35_slots"] < 1.0
+    # frac is the hardware issue-slot utilisation (live events/s x executed instructions per event of the committed
+    # ncu capture), not the canonical-budget figure: below 1 by construction, and below the dispatch-slot figure
+    assert 0.3 < r["frac"] < 1.0 and r["frac"] < r["frac_dispatch"] < 1.0 and r["frac_canonical_88"] > r["frac"]
+    assert r["traffic"] is not None and r["ncu_capture"]["matches_this_run"]
+    assert d["scaling"] == "weak"
+    # the fixed-range tally hash: the torch-stream path and the library's own host path give the same words
+    c = d["checks"]
+    assert len(c["tally_hash"]) == 16 and c["tally_hash"] == c["tally_hash_library_path"]
     assert "workload" in d["config"] and "BASELINE configs[1]" in d["config"]["workload"]
     assert d["checks"]["tally_range_flag"] == 0 and abs(d["checks"]["absorbed_weight_per_photon"] - 1.0) < 1e-4

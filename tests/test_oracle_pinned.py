@@ -16,10 +16,10 @@ from conftest import GOLDEN
 EXACT = json.loads((GOLDEN / "ref_float_tallies.json").read_text())
 
 
-@pytest.mark.parametrize("name", ["default", "highalbedo", "finegrid", "headless"])
+@pytest.mark.parametrize("name", ["default", "highalbedo", "finegrid", "headless", "default_pcg"])
 def test_port_matches_golden_reference_bits(orc, name):
     g = EXACT[name]
-    r = orc.run_batch(g["config"], g["seed"], g["photons"], chunk=0, impl="port")
+    r = orc.run_batch(g["config"], g["seed"], g["photons"], chunk=0, impl="port", rng=g.get("rng", "libc"))
     heat = r["heat_f"].view(np.uint32)
     heat2 = r["heat2_f"].view(np.uint32)
     if "nonzero_shells" in g:
@@ -38,6 +38,17 @@ def test_port_matches_live_reference(orc, name, n):
         a = orc.run_batch(name, 777, n, chunk=chunk, impl="reference")
         b = orc.run_batch(name, 777, n, chunk=chunk, impl="port")
         assert np.array_equal(a["heat"], b["heat"]) and np.array_equal(a["heat2"], b["heat2"])
+
+
+def test_port_matches_live_reference_on_pcg(orc):
+    """The UNMODIFIED photon.c compiled with -Drand=pcg31 (oracle/Makefile) against the port on the
+    same PCG32: bit for bit, so the port is pinned to the reference under two generators."""
+    if not (orc.REF_DIR / "libphoton_pcg_default.so").exists():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    for name, n in (("default", 3000), ("highalbedo", 40), ("finegrid", 3000)):
+        a = orc.run_batch(name, 31, n, chunk=0, impl="reference_pcg")
+        b = orc.run_batch(name, 31, n, chunk=0, impl="port", rng="pcg")
+        assert np.array_equal(a["heat_f"], b["heat_f"]) and np.array_equal(a["heat2_f"], b["heat2_f"])
 
 
 def test_port_invariants_default(orc):
@@ -131,6 +142,30 @@ def test_libc_rand_biases_the_reference_itself():
         assert np.abs(z0).max() < 4.0 and abs(z0.mean()) < 0.5
 
 
+def test_two_sound_generators_agree_where_libc_rand_does_not():
+    """The evidence behind leaving the literal libc stream at scale rests on two unrelated sound
+    generators: the port on xoshiro256** and the UNMODIFIED reference object code on PCG32
+    (1.3e8 photons each) agree in every shell, for all three optics and per 5 um shell of
+    config 5, while the unmodified reference on libc rand() is > 8 sigma away from PCG32 too."""
+    from stats import batch_means_z
+
+    for name in ("default", "highalbedo", "finegrid"):
+        xo = np.load(GOLDEN / f"port_xoshiro_batches_{name}.npz")
+        pcg = np.load(GOLDEN / f"ref_pcg_batches_{name}.npz")
+        z, ok = batch_means_z(xo["heat"], int(xo["photons_per_batch"]), pcg["heat"], int(pcg["photons_per_batch"]), min_mean=1e-4)
+        assert ok.sum() >= (101 if name != "finegrid" else 16)
+        assert np.abs(z[ok]).max() < 4.0 and abs(z[ok].mean()) < 0.5 and np.sqrt((z[ok] ** 2).mean()) < 1.3, (name, z)
+    libc = np.load(GOLDEN / "ref_batches_default.npz")
+    pcg = np.load(GOLDEN / "ref_pcg_batches_default.npz")
+    z, ok = batch_means_z(pcg["heat"], int(pcg["photons_per_batch"]), libc["heat"], int(libc["photons_per_batch"]))
+    assert np.abs(z).max() > 6.0 and z[5:40].mean() < -1.5 and z[60:].mean() > 3.0      # same shape as against xoshiro
+    a = np.load(GOLDEN / "port_xoshiro_pershell_finegrid.npz")
+    b = np.load(GOLDEN / "ref_pcg_pershell_finegrid.npz")
+    ok = np.maximum(a["mean"], b["mean"]) >= 1e-5
+    z = (a["mean"] - b["mean"])[ok] / np.sqrt(a["var_of_mean"] + b["var_of_mean"])[ok]
+    assert ok.sum() > 1400 and np.abs(z).max() < 4.0 and abs(np.sqrt((z ** 2).mean()) - 1.0) < 0.1
+
+
 def test_replay_agrees_with_reference_walk_on_sound_rng(orc):
     """tmc-stream-4 (Philox, direct direction sampling, fixed-point weights) vs the reference walk
     (photon_port.c: rejection sampling, float weights) on xoshiro256**: every shell within 4 sigma."""
@@ -199,3 +234,28 @@ def test_word_to_variate_mappings_have_no_singularities(orc):
     assert np.array_equal(cos, (2 * np.arange(256) + 1) / 256.0 - 1.0)          # exact midpoints
     assert cos.sum() == 0.0 and abs((cos**2).mean() * 3 - 1.0) < 1.6e-5 and np.abs(cos).max() < 1.0
     assert l.orc_costheta_of_word(0xFFFF00FF) == cos[0]                          # only bits 8..15 matter
+
+
+def test_batch_means_stderr_estimates_the_per_photon_spread(orc):
+    """SURVEY §8f rank 1.  The reference's Error column (tiny_mc.c:64) wants the standard error of heat[s]
+    but photon.c:31 accumulates squares per EVENT: the per-PHOTON second moment sum X_s^2 (X_s = one photon's total
+    deposit in shell s; orc_replay_per_photon) is what it needs.  On the same 2^17 photons: (1) the batch-means
+    variance of 64 batches - what the product reports (TMC_JSON, tmc_photons_fx_batches) - agrees with the
+    per-photon estimator; (2) the literal per-event estimator is 10-50 % too small in every shell and negative
+    (NaN in the printout) for the overflow shell."""
+    n, nb = 1 << 17, 64
+    heat, sq = orc.replay_per_photon("default", 7, 0, n)
+    var_true = (sq / n - (heat / n) ** 2) / n
+    assert (var_true > 0).all()
+    per = np.stack([orc.fx_to_float64("default", *orc.replay("default", 7, b * (n // nb), n // nb)[:2])[0] for b in range(nb)]) / (n // nb)
+    assert np.allclose(per.mean(axis=0) * n, heat, rtol=1e-12)
+    var_bm = per.var(axis=0, ddof=1) / nb
+    ratio = var_bm / var_true
+    assert 0.5 < ratio.min() and ratio.max() < 1.7              # 64 batches: each ratio is chi^2_63 / 63 (sd 0.18)
+    assert abs(ratio.mean() - 1.0) < 0.06
+    hfx, h2fx, _ = orc.replay("default", 7, 0, n)
+    h, h2 = orc.fx_to_float64("default", hfx, h2fx)
+    var_literal = (h2 - h * h / n) / n / n                      # tiny_mc.c:64, squared
+    assert var_literal[-1] < 0                                  # sqrt -> NaN for the overflow shell
+    under = np.sqrt(var_true[:-1] / var_literal[:-1])
+    assert under.min() > 1.05 and under.max() < 1.75

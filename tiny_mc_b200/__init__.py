@@ -11,6 +11,7 @@ from .capi import (  # noqa: F401
     RunInfo,
     Scales,
     TinyMcError,
+    device_tallies_check,
     fx_accumulate,
     fx_scales,
     generation_plan,
@@ -22,6 +23,7 @@ from .capi import (  # noqa: F401
     photons,
     photons_device,
     photons_fx,
+    photons_fx_batches,
     prepare,
     set_option,
 )

@@ -77,6 +77,7 @@ EXPORTS = (
     "tmc_init", "tmc_prepare", "tmc_finalize", "tmc_device_count", "tmc_last_error", "tmc_version",
     "tmc_abi_version", "tmc_set_option", "tmc_photons", "tmc_photons_fx", "tmc_photons_device",
     "tmc_fx_scales", "tmc_fx_accumulate", "tmc_generation_plan", "tmc_last_run_info",
+    "tmc_photons_fx_batches", "tmc_device_tallies_check",
 )
 
 _lib = None
@@ -104,6 +105,8 @@ def load() -> C.CDLL:
     lib.tmc_photons.argtypes = [C.POINTER(Params), u64, u64, u64, p, p]
     lib.tmc_photons_fx.argtypes = [C.POINTER(Params), u64, u64, u64, p, p]
     lib.tmc_photons_device.argtypes = [C.POINTER(Params), u64, u64, u64, C.c_int, p, p]
+    lib.tmc_photons_fx_batches.argtypes = [C.POINTER(Params), u64, u64, u64, C.c_uint32, p, p]
+    lib.tmc_device_tallies_check.argtypes = [C.POINTER(Params), C.c_int, p, p]
     lib.tmc_fx_scales.argtypes = [C.POINTER(Params), C.POINTER(Scales)]
     lib.tmc_fx_accumulate.argtypes = [C.POINTER(Params), p, p, p, p]
     lib.tmc_last_run_info.argtypes = [C.POINTER(RunInfo)]
@@ -171,6 +174,21 @@ def photons_device(cfg, seed: int, first_photon: int, n_photons: int, device: in
     """Asynchronous device-resident form: add into a device uint64[2*SHELLS+4] buffer."""
     p = make_params(cfg)
     _check(load().tmc_photons_device(C.byref(p), seed, first_photon, n_photons, int(device), C.c_void_p(d_tallies_ptr), C.c_void_p(stream_ptr)))
+
+
+def photons_fx_batches(cfg, seed: int, first_photon: int, n_photons: int, n_batches: int):
+    """n_batches consecutive sub-ranges in one pass: (heat_fx, heat2_fx) as uint64[n_batches, SHELLS]."""
+    p = make_params(cfg)
+    heat_fx = np.zeros((n_batches, p.shells), np.uint64)
+    heat2_fx = np.zeros((n_batches, p.shells), np.uint64)
+    _check(load().tmc_photons_fx_batches(C.byref(p), seed, first_photon, n_photons, n_batches, heat_fx.ctypes.data, heat2_fx.ctypes.data))
+    return heat_fx, heat2_fx
+
+
+def device_tallies_check(cfg, device: int, d_tallies_ptr: int, stream_ptr: int = 0):
+    """Raise TinyMcError(5) when the range flag of a device tally buffer is set (mandatory after photons_device)."""
+    p = make_params(cfg)
+    _check(load().tmc_device_tallies_check(C.byref(p), int(device), C.c_void_p(d_tallies_ptr), C.c_void_p(stream_ptr)))
 
 
 def fx_scales(cfg) -> Scales:

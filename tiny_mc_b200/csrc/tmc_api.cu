@@ -176,6 +176,19 @@ int deposit_table(int device, const Plan& pl, const uint2** out)
             *out = t.d_table;
             return TMC_OK;
         }
+    // bounded cache (parameter sweeps): beyond kMaxTablesPerDevice optics the oldest table of this device
+    // goes, after every kernel that may still read it has finished
+    constexpr size_t kMaxTablesPerDevice = 16;
+    size_t mine = 0;
+    for (const DepositTable& t : g_deposit_tables) mine += t.device == device;
+    if (mine >= kMaxTablesPerDevice)
+        for (size_t i = 0; i < g_deposit_tables.size(); ++i)
+            if (g_deposit_tables[i].device == device) {
+                CUDA_TRY(cudaDeviceSynchronize());
+                CUDA_TRY(cudaFree(g_deposit_tables[i].d_table));
+                g_deposit_tables.erase(g_deposit_tables.begin() + static_cast<long>(i));
+                break;
+            }
     const tmc::GenPlan& last = pl.gen[pl.n_gen - 1];
     std::vector<uint2> h(static_cast<size_t>(last.first_event) + last.n_events, make_uint2(0u, 0u));
     for (uint32_t g = 0; g < pl.n_gen; ++g) {
@@ -288,6 +301,19 @@ int queue_scratch(int device, cudaStream_t stream, size_t bytes, uint32_t** out)
             *out = q.d_buf;
             return TMC_OK;
         }
+    // bounded: a host that keeps creating and destroying streams must not grow this list for ever
+    // (a destroyed stream's handle may be reused by a later stream, which then simply inherits the buffer)
+    constexpr size_t kMaxScratchPerDevice = 32;
+    size_t mine = 0;
+    for (const QueueScratch& q : g_queue_scratch) mine += q.device == device;
+    if (mine >= kMaxScratchPerDevice)
+        for (size_t i = 0; i < g_queue_scratch.size(); ++i)
+            if (g_queue_scratch[i].device == device) {
+                CUDA_TRY(cudaDeviceSynchronize());
+                CUDA_TRY(cudaFree(g_queue_scratch[i].d_buf));
+                g_queue_scratch.erase(g_queue_scratch.begin() + static_cast<long>(i));
+                break;
+            }
     uint32_t* d = nullptr;
     CUDA_TRY(cudaMalloc(&d, bytes));
     g_queue_scratch.push_back(QueueScratch{ device, stream, d, bytes });
@@ -379,6 +405,7 @@ int kernel_occupancy(KernelFn fn, int block, size_t smem, int* per_sm)
     CUDA_TRY(cudaFuncGetAttributes(&fattr, fn));
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - static_cast<int>(fattr.sharedSizeBytes)));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, block, smem));
+    if (g_kernel_facts.size() >= 1024) g_kernel_facts.clear();    // plain numbers, recomputed on demand (SHELLS sweeps)
     g_kernel_facts.push_back(KernelFacts{ fn, dev, block, smem, *per_sm });
     return TMC_OK;
 }
@@ -566,36 +593,54 @@ int ensure_buffers(size_t words)
     return TMC_OK;
 }
 
-// One pass over [first, first+count): launch on every device, reduce, copy back.
-// On success `out` (host, 2*shells+4 words) holds the summed buffer.
-int run_range(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t first, uint64_t count,
+// One photon range with its own tally words ("slot"): a whole call, or one batch of a batched call.
+struct Slot {
+    uint64_t first, count;
+};
+
+bool trace_enabled()
+{
+    static const bool on = std::getenv("TMC_TRACE") != nullptr;   // per-phase host timings on stderr
+    return on;
+}
+
+// One pass: every slot's range is sharded over the devices, EVERYTHING is enqueued before anything is
+// waited for (all launches of all devices, then the one reduce, then the one copy), and only then
+// does the host block.  On success `out` (host, slots * (2*shells+4) words) holds the summed buffers.
+int run_slots(const tmc_params* p, const Plan& pl, uint64_t seed, const std::vector<Slot>& slots,
               uint32_t flush_override, std::vector<unsigned long long>& out, double* kernel_ms)
 {
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
     const size_t words = 2ull * p->shells + 4ull;
+    const size_t total = words * slots.size();
     const int ng = static_cast<int>(g.devs.size());
-    int rc = ensure_buffers(words);
+    int rc = ensure_buffers(total);
     if (rc) return rc;
     LaunchCfg cfg0{};
     for (int i = 0; i < ng; ++i) {
         Device& d = g.devs[i];
-        const uint64_t lo = first + count / ng * i + (static_cast<uint64_t>(i) < count % ng ? i : count % ng);
-        const uint64_t n = count / ng + (static_cast<uint64_t>(i) < count % ng ? 1 : 0);
         CUDA_TRY(cudaSetDevice(d.id));
-        CUDA_TRY(cudaMemsetAsync(d.d_buf, 0, words * sizeof(unsigned long long), d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.d_buf, 0, total * sizeof(unsigned long long), d.stream));
         CUDA_TRY(cudaEventRecord(d.ev0, d.stream));
-        if (n > 0) {
-            rc = enqueue_walk(p, pl, seed, lo, n, d.sms, flush_override, d.d_buf, d.stream, i == 0 ? &cfg0 : nullptr);
+        for (size_t k = 0; k < slots.size(); ++k) {
+            const uint64_t count = slots[k].count;
+            const uint64_t lo = slots[k].first + count / ng * i + (static_cast<uint64_t>(i) < count % ng ? i : count % ng);
+            const uint64_t n = count / ng + (static_cast<uint64_t>(i) < count % ng ? 1 : 0);
+            if (n == 0) continue;
+            rc = enqueue_walk(p, pl, seed, lo, n, d.sms, flush_override, d.d_buf + k * words, d.stream, (i == 0 && k == 0) ? &cfg0 : nullptr);
             if (rc) return rc;
         }
         CUDA_TRY(cudaEventRecord(d.ev1, d.stream));
     }
+    const auto t1 = clk::now();
     const bool use_nccl = ng > 1 && g.opt.nccl_reduce && g.devs[0].comm;
     if (use_nccl) {
         // The single collective of the path: sum heat|heat2|counters (u64, exact) onto device 0.
         NCCL_TRY(g.nccl.GroupStart());
         for (int i = 0; i < ng; ++i) {
             Device& d = g.devs[i];
-            NCCL_TRY(g.nccl.Reduce(d.d_buf, d.d_buf, words, ncclUint64, ncclSum, 0, d.comm, d.stream));
+            NCCL_TRY(g.nccl.Reduce(d.d_buf, d.d_buf, total, ncclUint64, ncclSum, 0, d.comm, d.stream));
         }
         NCCL_TRY(g.nccl.GroupEnd());
     }
@@ -603,25 +648,47 @@ int run_range(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t first
     for (int i = 0; i < n_read; ++i) {
         Device& d = g.devs[i];
         CUDA_TRY(cudaSetDevice(d.id));
-        CUDA_TRY(cudaMemcpyAsync(g.h_pinned + i * words, d.d_buf, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_pinned + i * total, d.d_buf, total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
     }
+    const auto t2 = clk::now();
+    // device 0 last: with NCCL its stream ends with the reduce that needs every other device's kernel
     double worst = 0.0;
-    for (int i = 0; i < ng; ++i) {
+    for (int i = ng - 1; i >= 0; --i) {
         Device& d = g.devs[i];
-        CUDA_TRY(cudaSetDevice(d.id));
         CUDA_TRY(cudaStreamSynchronize(d.stream));
         float ms = 0.0f;
         CUDA_TRY(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
         if (ms > worst) worst = ms;
     }
-    out.assign(words, 0ull);
+    const auto t3 = clk::now();
+    out.assign(total, 0ull);
     for (int i = 0; i < n_read; ++i)
-        for (size_t w = 0; w < words; ++w) out[w] += g.h_pinned[i * words + w];
+        for (size_t w = 0; w < total; ++w) out[w] += g.h_pinned[i * total + w];
     *kernel_ms += worst;
     g.info.blocks_per_gpu = static_cast<uint32_t>(cfg0.grid);
     g.info.threads_per_block = static_cast<uint32_t>(cfg0.block);
     g.info.flush_iters = cfg0.flush_iters;
     g.info.smem_bytes = static_cast<uint32_t>(cfg0.smem);
+    if (trace_enabled()) {
+        auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        std::fprintf(stderr, "tmc trace: %d gpus, %zu slots: enqueue %.0f us, reduce+copy enqueue %.0f us, wait %.0f us (kernels %.0f us), sum %.0f us\n",
+                     ng, slots.size(), us(t0, t1), us(t1, t2), us(t2, t3), worst * 1e3, us(t3, clk::now()));
+    }
+    return TMC_OK;
+}
+
+int run_range(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t first, uint64_t count,
+              uint32_t flush_override, std::vector<unsigned long long>& out, double* kernel_ms)
+{
+    return run_slots(p, pl, seed, std::vector<Slot>{ Slot{ first, count } }, flush_override, out, kernel_ms);
+}
+
+// The counter words behind a slot's tallies: range flag and internal error -> status code.
+int check_counters(const tmc_params* p, const unsigned long long* slot_words)
+{
+    if (slot_words[2ull * p->shells + 3] != 0ull)
+        return fail(TMC_ERR_CUDA, "internal: the block's shared-memory window does not start where walk_kernel.cuh assumes");
+    if (slot_words[2ull * p->shells + 2] != 0ull) return TMC_ERR_TALLY_RANGE;
     return TMC_OK;
 }
 
@@ -648,9 +715,9 @@ int run_fx(const tmc_params* p, uint64_t seed, uint64_t first, uint64_t n, uint6
         for (int attempt = 0;; ++attempt) {
             rc = run_range(p, pl, seed, first + done, todo, flush_override, sum, &kernel_ms);
             if (rc) return rc;
-            if (sum[2ull * p->shells + 3] != 0ull)
-                return fail(TMC_ERR_CUDA, "internal: the block's shared-memory window does not start where walk_kernel.cuh assumes");
-            if (sum[2ull * p->shells + 2] == 0ull) break;
+            const int st = check_counters(p, sum.data());
+            if (st == TMC_OK) break;
+            if (st != TMC_ERR_TALLY_RANGE) return st;
             if (attempt == 3 || g.info.flush_iters <= 1u)
                 return fail(TMC_ERR_TALLY_RANGE, "a shared tally exceeded 2^31 within %u iterations", g.info.flush_iters);
             flush_override = g.info.flush_iters / 8u ? g.info.flush_iters / 8u : 1u;
@@ -663,6 +730,61 @@ int run_fx(const tmc_params* p, uint64_t seed, uint64_t first, uint64_t n, uint6
         g.info.events += sum[2ull * p->shells];
         g.info.photons += sum[2ull * p->shells + 1];
         done += todo;
+    }
+    g.info.kernel_ms = kernel_ms;
+    g.info.call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (g.info.photons != n) return fail(TMC_ERR_CUDA, "internal: simulated %llu photons, expected %llu", (unsigned long long)g.info.photons, (unsigned long long)n);
+    return TMC_OK;
+}
+
+// n_batches consecutive sub-ranges of [first, first + n), each into its OWN tally arrays, in one pass:
+// every batch is sharded over all devices, all launches are enqueued back to back, one reduce and one
+// copy bring all batches home (the per-call costs are paid once, not n_batches times).
+int run_fx_batches(const tmc_params* p, uint64_t seed, uint64_t first, uint64_t n, uint32_t n_batches, uint64_t* heat_fx, uint64_t* heat2_fx)
+{
+    if (!g.inited) return fail(TMC_ERR_NO_DEVICE, "tmc_init has not been called (or found no sm_100 GPU)");
+    if (!heat_fx || !heat2_fx) return fail(TMC_ERR_BAD_ARG, "tally pointer is NULL");
+    if (n_batches < 1u || n_batches > 4096u) return fail(TMC_ERR_BAD_ARG, "n_batches must be 1..4096");
+    Plan pl;
+    int rc = make_plan(p, &pl);
+    if (rc) return rc;
+    if ((n + n_batches - 1) / n_batches > (1ull << (62 - pl.sc.heat_shift)))
+        return fail(TMC_ERR_BAD_ARG, "batches of more than 2^%u photons would overflow the 64-bit tallies; use more batches", 62 - pl.sc.heat_shift);
+    const auto t0 = std::chrono::steady_clock::now();
+    g.info = tmc_run_info{};
+    g.info.n_gpus = static_cast<uint32_t>(g.devs.size());
+    g.info.philox_rounds = static_cast<uint32_t>(g.opt.philox_rounds);
+    std::vector<Slot> slots(n_batches);
+    uint64_t lo = first;
+    for (uint32_t b = 0; b < n_batches; ++b) {        // the same split as shards.py / run_slots
+        const uint64_t cnt = n / n_batches + (b < n % n_batches ? 1 : 0);
+        slots[b] = Slot{ lo, cnt };
+        lo += cnt;
+    }
+    const size_t words = 2ull * p->shells + 4ull;
+    std::vector<unsigned long long> sum;
+    double kernel_ms = 0.0;
+    uint32_t flush_override = 0;
+    for (int attempt = 0;; ++attempt) {
+        rc = run_slots(p, pl, seed, slots, flush_override, sum, &kernel_ms);
+        if (rc) return rc;
+        int st = TMC_OK;
+        for (uint32_t b = 0; b < n_batches && st == TMC_OK; ++b) st = check_counters(p, sum.data() + b * words);
+        if (st == TMC_OK) break;
+        if (st != TMC_ERR_TALLY_RANGE) return st;
+        if (attempt == 3 || g.info.flush_iters <= 1u)
+            return fail(TMC_ERR_TALLY_RANGE, "a shared tally exceeded 2^31 within %u iterations", g.info.flush_iters);
+        flush_override = g.info.flush_iters / 8u ? g.info.flush_iters / 8u : 1u;
+        g.info.retries += 1;
+    }
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        const unsigned long long* w = sum.data() + b * words;
+        for (uint32_t sh = 0; sh < p->shells; ++sh) {
+            heat_fx[static_cast<size_t>(b) * p->shells + sh] += w[sh];
+            heat2_fx[static_cast<size_t>(b) * p->shells + sh] += w[p->shells + sh];
+        }
+        g.info.events += w[2ull * p->shells];
+        g.info.photons += w[2ull * p->shells + 1];
     }
     g.info.kernel_ms = kernel_ms;
     g.info.call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -726,9 +848,22 @@ int tmc_finalize(void)
     return TMC_OK;
 }
 
+static int init_devices(int n_gpus);
+
 int tmc_init(int n_gpus)
 {
-    if (g.inited) tmc_finalize();
+    tmc_finalize();                     // also releases whatever a failed earlier attempt left behind
+    const int rc = init_devices(n_gpus);
+    if (rc) {
+        const std::string why = g.err;
+        tmc_finalize();                 // streams, events and communicators created before the failure
+        g.err = why;
+    }
+    return rc;
+}
+
+static int init_devices(int n_gpus)
+{
     int visible = 0;
     cudaError_t e = cudaGetDeviceCount(&visible);
     if (e != cudaSuccess || visible < 1)
@@ -741,7 +876,7 @@ int tmc_init(int n_gpus)
         d = Device{};
         d.id = i;
         int rc = check_device_arch(i);
-        if (rc) { g.devs.clear(); return rc; }
+        if (rc) return rc;
         CUDA_TRY(cudaSetDevice(i));
         CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, i));
         CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
@@ -851,6 +986,12 @@ int tmc_photons_fx(const tmc_params* p, uint64_t seed, uint64_t first_photon, ui
     return run_fx(p, seed, first_photon, n_photons, heat_fx, heat2_fx);
 }
 
+int tmc_photons_fx_batches(const tmc_params* p, uint64_t seed, uint64_t first_photon, uint64_t n_photons, uint32_t n_batches,
+                           uint64_t* heat_fx, uint64_t* heat2_fx)
+{
+    return run_fx_batches(p, seed, first_photon, n_photons, n_batches, heat_fx, heat2_fx);
+}
+
 int tmc_photons(const tmc_params* p, uint64_t seed, uint64_t first_photon, uint64_t n_photons, float* heats, float* heats_squared)
 {
     if (!heats || !heats_squared) return fail(TMC_ERR_BAD_ARG, "tally pointer is NULL");
@@ -887,6 +1028,22 @@ int tmc_photons_device(const tmc_params* p, uint64_t seed, uint64_t first_photon
     g.info.smem_bytes = static_cast<uint32_t>(cfg.smem);
     g.info.philox_rounds = static_cast<uint32_t>(g.opt.philox_rounds);
     return rc;
+}
+
+int tmc_device_tallies_check(const tmc_params* p, int device, const void* d_tallies, void* cuda_stream)
+{
+    if (!p || !d_tallies) return fail(TMC_ERR_BAD_ARG, "NULL pointer");
+    unsigned long long counters[4] = { 0ull, 0ull, 0ull, 0ull };
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMemcpyAsync(counters, static_cast<const unsigned long long*>(d_tallies) + 2ull * p->shells, sizeof counters,
+                             cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(cuda_stream)));
+    CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+    if (counters[3] != 0ull)
+        return fail(TMC_ERR_CUDA, "internal: the block's shared-memory window does not start where walk_kernel.cuh assumes");
+    if (counters[2] != 0ull)
+        return fail(TMC_ERR_TALLY_RANGE, "a shared tally exceeded its 32-bit range check: the tallies in this buffer are invalid; "
+                                         "zero the buffer and repeat the range with a smaller \"flush_iters\" option");
+    return TMC_OK;
 }
 
 int tmc_last_run_info(tmc_run_info* out)

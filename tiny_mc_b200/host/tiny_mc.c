@@ -4,7 +4,8 @@
  * (reference tiny_mc.c:34-69); the per-photon loop `for (i < PHOTONS) photon(heat, heat2)`
  * (reference tiny_mc.c:47-49) becomes ONE call of tmc_photons().  Host code stays plain C11.
  *
- * Environment: TMC_GPUS=<n> selects how many GPUs to use (default: all visible);
+ * Environment: TMC_GPUS=<n> selects how many GPUs to use (default: all visible); TMC_NCCL=0 sums the
+ * per-GPU tally words on the host instead of with ncclReduce; TMC_TRACE=1 prints per-phase host timings;
  * TMC_JSON=<path> additionally writes the exact tallies in machine-readable form (SURVEY §8f
  * rank 1: the float printout of the reference loses digits at large PHOTONS; the reference's
  * own stdout contract is untouched).
@@ -27,38 +28,41 @@ static float heat2[SHELLS];
 static uint64_t heat_fx[SHELLS];
 static uint64_t heat2_fx[SHELLS];
 
-/* batch-means standard error of the per-photon mean heat of every shell (filled when TMC_JSON is set):
- * the estimator the reference's Error column (tiny_mc.c:64) is not - that one sums squares per EVENT and is
- * NaN-prone.  Splitting the range changes nothing else: the sum of the batches is bit-identical. */
-#define TMC_BATCHES 16
+/* Batch-means standard error of the per-photon mean heat of every shell (filled when TMC_JSON is set):
+ * the estimator the reference's Error column (tiny_mc.c:64) is not - that one sums squares per EVENT, so it
+ * under-estimates the spread of the per-PHOTON shell sums and is NaN-prone.  The variance of
+ * TMC_BATCHES batch means estimates Var(mean heat) without bias whatever the correlation between the events of
+ * one photon; its own relative precision is 1/sqrt(2 (TMC_BATCHES-1)) = 9 %.  One library call walks all
+ * batches (tmc_photons_fx_batches); their sum is bit-identical to the unsplit run. */
+#define TMC_BATCHES 64
 static double heat_stderr[SHELLS];
 static int have_stderr = 0;
 
 static int walk_in_batches(const tmc_params* params, uint64_t seed, uint64_t photons)
 {
-    static uint64_t b_heat[SHELLS], b_heat2[SHELLS];
-    static double sum[SHELLS], sum_sq[SHELLS];
-    uint64_t done = 0;
-    for (int b = 0; b < TMC_BATCHES; ++b) {
-        const uint64_t n = photons / TMC_BATCHES + ((uint64_t)b < photons % TMC_BATCHES ? 1 : 0);
-        for (unsigned i = 0; i < SHELLS; ++i) b_heat[i] = b_heat2[i] = 0;
-        const int rc = tmc_photons_fx(params, seed, done, n, b_heat, b_heat2);
-        if (rc != TMC_OK) return rc;
+    uint64_t* b_heat = calloc((size_t)TMC_BATCHES * SHELLS, sizeof(uint64_t));
+    uint64_t* b_heat2 = calloc((size_t)TMC_BATCHES * SHELLS, sizeof(uint64_t));
+    if (!b_heat || !b_heat2) return TMC_ERR_BAD_ARG;
+    const int rc = tmc_photons_fx_batches(params, seed, 0, photons, TMC_BATCHES, b_heat, b_heat2);
+    if (rc == TMC_OK) {
         for (unsigned i = 0; i < SHELLS; ++i) {
-            const double m = n ? (double)b_heat[i] / (double)n : 0.0;
-            heat_fx[i] += b_heat[i];
-            heat2_fx[i] += b_heat2[i];
-            sum[i] += m;
-            sum_sq[i] += m * m;
+            double sum = 0.0, sum_sq = 0.0;
+            for (unsigned b = 0; b < TMC_BATCHES; ++b) {
+                const uint64_t n = photons / TMC_BATCHES + ((uint64_t)b < photons % TMC_BATCHES ? 1 : 0);
+                const double m = (double)b_heat[(size_t)b * SHELLS + i] / (double)n;
+                heat_fx[i] += b_heat[(size_t)b * SHELLS + i];
+                heat2_fx[i] += b_heat2[(size_t)b * SHELLS + i];
+                sum += m;
+                sum_sq += m * m;
+            }
+            const double mean = sum / TMC_BATCHES, var = (sum_sq / TMC_BATCHES - mean * mean) * TMC_BATCHES / (TMC_BATCHES - 1.0);
+            heat_stderr[i] = sqrt((var > 0.0 ? var : 0.0) / TMC_BATCHES);
         }
-        done += n;
+        have_stderr = 1;
     }
-    for (unsigned i = 0; i < SHELLS; ++i) {
-        const double mean = sum[i] / TMC_BATCHES, var = (sum_sq[i] / TMC_BATCHES - mean * mean) * TMC_BATCHES / (TMC_BATCHES - 1.0);
-        heat_stderr[i] = sqrt((var > 0.0 ? var : 0.0) / TMC_BATCHES);
-    }
-    have_stderr = 1;
-    return TMC_OK;
+    free(b_heat);
+    free(b_heat2);
+    return rc;
 }
 
 static void write_json(const char* path, const tmc_params* params, uint64_t seed, uint64_t photons, double seconds)
@@ -81,7 +85,7 @@ static void write_json(const char* path, const tmc_params* params, uint64_t seed
     fprintf(f, "],\n \"heat2\": [");
     for (unsigned i = 0; i < SHELLS; ++i) fprintf(f, "%s%.17g", i ? ", " : "", (double)heat2_fx[i] * s2);
     if (have_stderr) {
-        fprintf(f, "],\n \"heat_per_photon_stderr_fx_units\": [");
+        fprintf(f, "],\n \"stderr_batches\": %d,\n \"heat_per_photon_stderr_fx_units\": [", TMC_BATCHES);
         for (unsigned i = 0; i < SHELLS; ++i) fprintf(f, "%s%.9g", i ? ", " : "", heat_stderr[i]);
     }
     fprintf(f, "],\n \"heat_fx\": [");
@@ -98,6 +102,7 @@ int main(void)
     tmc_report_heading(stdout, "B200 version (tiny_mc_b200: sm_100a persistent-thread walk, Philox4x32 per photon)",
                        MU_S, MU_A, photons);
 
+    if (getenv("TMC_NCCL")) tmc_set_option("nccl_reduce", atoi(getenv("TMC_NCCL")));   /* 0: sum the per-GPU words on the host */
     const char* env = getenv("TMC_GPUS");
     if (tmc_init(env ? atoi(env) : 0) != TMC_OK) { /* one-off, outside the timed region */
         fprintf(stderr, "tiny_mc_b200: %s\n", tmc_last_error());

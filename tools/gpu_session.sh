@@ -40,6 +40,16 @@ r2a)
     TMC_LIB=tiny_mc_b200/lib/exp/libtinymc_$v.so timeout 300 python tools/quick_bench.py default:0:0 default:768:1 default:1024:1 highalbedo:0:0 finegrid:0:0 >> gpurun_out/quick_variants.jsonl 2>> gpurun_out/quick.err; echo "variant $v rc=$?"
   done
   cat gpurun_out/quick_variants.jsonl ;;
+scale)   # usage: gpurun --gpus N -- 'NGPU=N bash tools/gpu_session.sh scale'
+  n=${NGPU:-2}
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 \
+      bench.py --gpus $n --steps ${STEPS:-5} --warmup 3 > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err; echo "scale n=$n rc=$?"; cat gpurun_out/scale_n$n.json
+  timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "multi_gpu or batches" > gpurun_out/pytest_multigpu_n$n.log 2>&1; echo "pytest multi rc=$?"; tail -3 gpurun_out/pytest_multigpu_n$n.log
+  for prog in headless_config3; do
+    TMC_TRACE=1 TMC_GPUS=$n timeout 300 tiny_mc_b200/bin/$prog > gpurun_out/${prog}_n$n.txt 2> gpurun_out/${prog}_n$n.err; echo "$prog rc=$?"; head -8 gpurun_out/${prog}_n$n.txt; tail -3 gpurun_out/${prog}_n$n.err
+    TMC_TRACE=1 TMC_GPUS=$n TMC_JSON=gpurun_out/${prog}_n$n.json timeout 300 tiny_mc_b200/bin/$prog > gpurun_out/${prog}_json_n$n.txt 2> gpurun_out/${prog}_json_n$n.err; echo "$prog json rc=$?"; head -8 gpurun_out/${prog}_json_n$n.txt; tail -3 gpurun_out/${prog}_json_n$n.err
+    TMC_TRACE=1 TMC_GPUS=$n TMC_NCCL=0 timeout 300 tiny_mc_b200/bin/$prog > gpurun_out/${prog}_hostsum_n$n.txt 2> gpurun_out/${prog}_hostsum_n$n.err; echo "$prog hostsum rc=$?"; head -8 gpurun_out/${prog}_hostsum_n$n.txt | tail -3; tail -2 gpurun_out/${prog}_hostsum_n$n.err
+  done ;;
 quick)
   timeout 600 python tools/quick_bench.py > gpurun_out/quick.jsonl 2> gpurun_out/quick.err; echo "quick rc=$?"; cat gpurun_out/quick.jsonl ;;
 sweep)
