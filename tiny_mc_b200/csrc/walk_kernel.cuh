@@ -39,6 +39,9 @@
 
 #include "philox.cuh"
 
+#ifndef TMC_GROUP
+#define TMC_GROUP 4        /* events of a Philox block whose table look-ups are issued together (walk loop) */
+#endif
 #ifndef TMC_EXPERIMENT
 #define TMC_EXPERIMENT 0   /* timing experiments (tools/experiments.sh); the product is built with 0 */
 #endif
@@ -378,16 +381,96 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
 #pragma unroll
                 for (int k = 0; k < 4; ++k) r[j][k] = cur[j][k];
         };
+        // A full block: its four events for every photon of the lane, software-pipelined in SOURCE order.
+        // ptxas may not move a shared-memory load (direction table) above an earlier shared-memory atomic
+        // (tallies): it cannot know that the two never alias.  Written event by event, every table look-up
+        // would therefore wait for the previous event's atomics, and the events of a warp would run as one
+        // serial chain (SHF -> FADD -> MUFU -> FMUL -> FFMA x5 -> MUFU -> FFMA.RZ -> VIMNMX -> PRMT -> ATOMS,
+        // ~60 cycles of fixed latencies each).  So: all look-ups and logarithms of a group of TMC_GROUP events
+        // first (independent of each other), then the position chain and the radii, then the atomics; the
+        // next group's look-ups are issued BEFORE this group's atomics.
         auto four_events = [&](uint32_t (&cur)[PPL][4]) {
             take_block(cur);
-            absorb();
-            event(IntTag<0>{}, partial_tag, dep, dep2);
-            absorb();
-            event(IntTag<1>{}, partial_tag, dep, dep2);
-            absorb();
-            event(IntTag<2>{}, partial_tag, dep, dep2);
-            absorb();
-            event(IntTag<3>{}, partial_tag, dep, dep2);
+            constexpr int G = TMC_GROUP;                     // events per group: 1, 2 or 4
+            float L[G][PPL];
+            float2 pol[G][PPL], azi[G][PPL];
+            uint32_t off[G][PPL];
+            auto look_up = [&](auto first_tag) {
+                constexpr int S0 = decltype(first_tag)::value;
+#pragma unroll
+                for (int e = 0; e < G; ++e)
+#pragma unroll
+                    for (int j = 0; j < PPL; ++j) {
+                        const uint32_t v = r[j][S0 + e];
+                        L[e][j] = mufu_lg2(__uint_as_float(__funnelshift_r(v, 0x7Fu, 9)) - kOneMinusHalfUlp);
+                        pol[e][j] = lds_f32x2<kSmemTableAbs>(row_offset<1>(v, polar_low));
+                        if constexpr (!RADIAL) azi[e][j] = lds_f32x2<kSmemTableAbs>(row_offset<0>(v, azimuth_low));
+                    }
+            };
+            auto walk_group = [&]() {
+#pragma unroll
+                for (int e = 0; e < G; ++e)
+#pragma unroll
+                    for (int j = 0; j < PPL; ++j) {
+                        float rad;
+                        if constexpr (RADIAL) {
+                            const float t = L[e][j] * -kLn2, tmu = L[e][j] * pol[e][j].x;
+                            const float r2 = fmaf(px[j] + px[j], tmu, fmaf(t, t, px[j] * px[j]));
+                            rad = mufu_sqrt(fmaxf(r2, 0.0f));
+                            px[j] = rad;
+                        } else {
+                            const float ts = L[e][j] * pol[e][j].y;
+                            px[j] = fmaf(L[e][j], pol[e][j].x, px[j]);
+                            py[j] = fmaf(ts, azi[e][j].x, py[j]);
+                            pz[j] = fmaf(ts, azi[e][j].y, pz[j]);
+                            rad = mufu_sqrt(fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j])));
+                        }
+                        const uint32_t sb = min(__float_as_uint(__fmaf_rz(rad, a.shells_per_mfp, 8388608.0f)), clamp_bits);
+                        off[e][j] = LANE_PRIVATE ? shell_offset(sb, lane_low) : (sb << 2) + plain_bias;
+                    }
+            };
+            auto tally_group = [&]() {
+#pragma unroll
+                for (int e = 0; e < G; ++e) {
+                    absorb();
+#pragma unroll
+                    for (int j = 0; j < PPL; ++j) {
+                        if (!PARTIAL || act[j]) {
+                            red_shared_add<kSmemBinsAbs>(off[e][j], dep);
+                            if constexpr (LANE_PRIVATE) red_shared_add<kSmemBinsAbs + 128u>(off[e][j], dep2);
+                            else red_shared_add<kSmemBinsAbs>(off[e][j] + heat2_off, dep2);
+                        }
+                    }
+                }
+            };
+            look_up(IntTag<0>{});
+            if constexpr (G == 4) {
+                walk_group();
+                tally_group();
+            } else if constexpr (G == 2) {
+                walk_group();
+                uint32_t off0[G][PPL];
+#pragma unroll
+                for (int e = 0; e < G; ++e)
+#pragma unroll
+                    for (int j = 0; j < PPL; ++j) off0[e][j] = off[e][j];
+                look_up(IntTag<2>{});                    // before the atomics of events 0-1
+#pragma unroll
+                for (int e = 0; e < G; ++e) {
+                    absorb();
+#pragma unroll
+                    for (int j = 0; j < PPL; ++j)
+                        if (!PARTIAL || act[j]) {
+                            red_shared_add<kSmemBinsAbs>(off0[e][j], dep);
+                            if constexpr (LANE_PRIVATE) red_shared_add<kSmemBinsAbs + 128u>(off0[e][j], dep2);
+                            else red_shared_add<kSmemBinsAbs>(off0[e][j] + heat2_off, dep2);
+                        }
+                }
+                walk_group();
+                tally_group();
+            } else {
+                static_assert(G == 2 || G == 4, "TMC_GROUP must be 2 or 4");
+            }
         };
         auto maybe_drain = [&](uint32_t blocks) {
             blocks_since_drain += blocks;

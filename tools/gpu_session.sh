@@ -50,6 +50,22 @@ scale)   # usage: gpurun --gpus N -- 'NGPU=N bash tools/gpu_session.sh scale'
     TMC_TRACE=1 TMC_GPUS=$n TMC_JSON=gpurun_out/${prog}_n$n.json timeout 300 tiny_mc_b200/bin/$prog > gpurun_out/${prog}_json_n$n.txt 2> gpurun_out/${prog}_json_n$n.err; echo "$prog json rc=$?"; head -8 gpurun_out/${prog}_json_n$n.txt; tail -3 gpurun_out/${prog}_json_n$n.err
     TMC_TRACE=1 TMC_GPUS=$n TMC_NCCL=0 timeout 300 tiny_mc_b200/bin/$prog > gpurun_out/${prog}_hostsum_n$n.txt 2> gpurun_out/${prog}_hostsum_n$n.err; echo "$prog hostsum rc=$?"; head -8 gpurun_out/${prog}_hostsum_n$n.txt | tail -3; tail -2 gpurun_out/${prog}_hostsum_n$n.err
   done ;;
+variants)   # quick_bench of the in-tree library and of every tiny_mc_b200/lib/exp/libtinymc_*.so
+  timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "replay or other_optics or independent_of_split or single_photon" > gpurun_out/pytest_replay.log 2>&1; echo "pytest replay rc=$?"; tail -3 gpurun_out/pytest_replay.log
+  rm -f gpurun_out/quick_variants.jsonl
+  timeout 300 python tools/quick_bench.py ${PLANS:-default:0:0 default:768:1 default:1024:1 highalbedo:0:0:10:22 finegrid:0:0 finegrid:512:1} >> gpurun_out/quick_variants.jsonl 2>> gpurun_out/quick.err
+  for f in tiny_mc_b200/lib/exp/libtinymc_*.so; do
+    [ -e "$f" ] || continue
+    TMC_LIB=$f timeout 300 python tools/quick_bench.py ${PLANS:-default:0:0 default:768:1 default:1024:1 highalbedo:0:0:10:22 finegrid:0:0 finegrid:512:1} >> gpurun_out/quick_variants.jsonl 2>> gpurun_out/quick.err; echo "variant $f rc=$?"
+  done
+  python - <<'PY'
+import json
+for l in open("gpurun_out/quick_variants.jsonl"):
+    d = json.loads(l)
+    if "error" in d: print(d); continue
+    print(f"{d['lib'] or 'in-tree':28s} {d['config']:10s} block {d['block']:4d} x grid {d['grid']:3d} flush {d['flush']:4d}  {d['photons_per_s']:.4g} photons/s  {d['events_per_s']:.4g} events/s")
+PY
+  ;;
 quick)
   timeout 600 python tools/quick_bench.py > gpurun_out/quick.jsonl 2> gpurun_out/quick.err; echo "quick rc=$?"; cat gpurun_out/quick.jsonl ;;
 sweep)
