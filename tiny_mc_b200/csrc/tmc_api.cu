@@ -350,6 +350,7 @@ struct LaunchCfg {
     KernelFn fn;
     int block;
     int grid;
+    int full_grid;   // the grid a launch that fills the device would use (>= grid)
     size_t smem;
     uint32_t flush_iters;
 };
@@ -442,6 +443,7 @@ int configure_launch(const tmc_params* p, const Plan& pl, int device_sms, uint64
     if (per_sm < 1) return fail(TMC_ERR_CUDA, "kernel does not fit on an SM (block=%d smem=%zu)", block, smem);
     if (g.opt.blocks_per_sm > 0 && g.opt.blocks_per_sm < per_sm) per_sm = g.opt.blocks_per_sm;
     uint64_t grid = static_cast<uint64_t>(device_sms) * per_sm;
+    cfg->full_grid = static_cast<int>(grid);
     const uint64_t warps = static_cast<uint64_t>(block) / 32u;
     const uint64_t cohort = 32ull * kPhotonsPerLane;
     const uint64_t needed = ((count + cohort - 1) / cohort + warps - 1) / warps;   // cohorts of photons, one per warp
@@ -524,7 +526,9 @@ int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t fi
         if (rc) return rc;
         if (!have_first && first_cfg) *first_cfg = cfg;
         have_first = true;
-        rc = queue_scratch(dev, stream, static_cast<size_t>(cfg.grid) * (cfg.block / 32) * tmc::kQueueBytesPerWarp, &a.queues);
+        // sized for a full grid of this block shape even when this launch is small (tmc_prepare's is): growing the
+        // buffer later would cost a stream synchronisation and a cudaFree / cudaMalloc inside a timed call
+        rc = queue_scratch(dev, stream, static_cast<size_t>(cfg.full_grid) * (cfg.block / 32) * tmc::kQueueBytesPerWarp, &a.queues);
         if (rc) return rc;
         a.first = first;
         a.count = n;

@@ -40,6 +40,22 @@ r2a)
     TMC_LIB=tiny_mc_b200/lib/exp/libtinymc_$v.so timeout 300 python tools/quick_bench.py default:0:0 default:768:1 default:1024:1 highalbedo:0:0 finegrid:0:0 >> gpurun_out/quick_variants.jsonl 2>> gpurun_out/quick.err; echo "variant $v rc=$?"
   done
   cat gpurun_out/quick_variants.jsonl ;;
+scaleall)   # on an 8-GPU box: the driver's scaling run (N = 1, 2, 4, 8 back to back)
+  timeout 600 python bench.py --no-cpu-baseline > gpurun_out/scale_n1.json 2> gpurun_out/scale_n1.err; echo "scale n=1 rc=$?"
+  for n in 2 4 8; do
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n \
+        bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err; echo "scale n=$n rc=$?"
+  done
+  python - <<'PY'
+import json
+for n in (1, 2, 4, 8):
+    try:
+        d = json.load(open(f"gpurun_out/scale_n{n}.json"))
+        print(n, f"value {d['value']:.4g} e2e {d['e2e']['value']:.4g} ms/step {d['ms_per_step']:.3f} hash {d['checks']['tally_hash']} lib {d['checks']['tally_hash_library_path']} launches {d['gpu_launches']}")
+    except Exception as e:
+        print(n, "failed", e)
+PY
+  ;;
 scale)   # usage: gpurun --gpus N -- 'NGPU=N bash tools/gpu_session.sh scale'
   n=${NGPU:-2}
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 \
