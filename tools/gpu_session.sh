@@ -28,6 +28,12 @@ ncucfg)
         python bench.py --config $c --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_$c.log 2>&1; echo "ncu $c rc=$?"
     timeout 600 python bench.py --config $c --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; echo "bench $c rc=$?"
   done ;;
+report)
+  timeout 900 python tools/parity_report.py > gpurun_out/parity.json 2> gpurun_out/parity.err; echo "parity rc=$?"; python -c "
+import json
+d = json.load(open('gpurun_out/parity.json'))
+for k, v in d.items(): print(k, {a: b for a, b in v.items() if a != 'z'})"
+  timeout 900 python tools/soak.py > gpurun_out/soak.jsonl 2> gpurun_out/soak.err; echo "soak rc=$?"; cat gpurun_out/soak.jsonl ;;
 sanitize)
   for t in memcheck racecheck initcheck; do timeout 900 compute-sanitizer --tool $t --error-exitcode 9 python tools/sanitize_run.py > gpurun_out/sanitizer_$t.log 2>&1; echo "sanitizer $t rc=$?"; tail -2 gpurun_out/sanitizer_$t.log; done ;;
 microncu)

@@ -15,15 +15,33 @@ from stats import batch_means_z, literal_sigma_z  # noqa: E402
 
 tmc.init(1)
 out = {}
+GOLD = ROOT / "tests" / "golden"
+# config 5 per 5 um shell, against both sound-generator references (256 batches of 2^20 GPU photons)
+nb, n = 256, 1 << 20
+bh, bh2 = tmc.photons_fx_batches("finegrid", 0xF19E, 0, nb * n, nb)
+per = np.stack([tmc.capi.fx_to_float64("finegrid", bh[b], bh2[b])[0] for b in range(nb)]) / n
+mean, var = per.mean(axis=0), per.var(axis=0, ddof=1) / nb
+for fixture in ("ref_pcg", "port_xoshiro"):
+    ref = np.load(GOLD / f"{fixture}_pershell_finegrid.npz")
+    ok = np.maximum(mean, ref["mean"]) >= 1e-5
+    z = (mean - ref["mean"])[ok] / np.sqrt(var + ref["var_of_mean"])[ok]
+    trend = z[: len(z) // 100 * 100].reshape(-1, 100).mean(axis=1)
+    out[f"finegrid_per_shell_vs_{fixture}"] = dict(
+        gpu_photons=nb * n, reference_photons=int(ref["batches"]) * int(ref["photons_per_batch"]), shells_tested=int(ok.sum()),
+        max_abs_z=float(np.abs(z).max()), rms_z=float(np.sqrt((z ** 2).mean())), mean_z=float(z.mean()),
+        shells_beyond_3_sigma=int((np.abs(z) > 3).sum()), mean_z_per_100_shells=[round(float(v), 2) for v in trend],
+        median_relative_sigma_per_shell=float(np.median(np.sqrt(var + ref["var_of_mean"])[ok] / mean[ok])))
 for name, nb, n in (("default", 64, 1 << 22), ("highalbedo", 64, 1 << 15), ("finegrid", 64, 1 << 22)):
-    ref = np.load(ROOT / "tests" / "golden" / f"port_xoshiro_batches_{name}.npz")
+    ref = np.load(GOLD / f"port_xoshiro_batches_{name}.npz")
     n_ref = int(ref["photons_per_batch"])
-    heat, heat2 = [], []
-    for b in range(nb):
-        h, h2 = tmc.capi.fx_to_float64(name, *tmc.photons_fx(name, 0x5EED, b * n, n))
-        heat.append(h)
-        heat2.append(h2)
-    heat, heat2 = np.stack(heat), np.stack(heat2)
+    bh, bh2 = tmc.photons_fx_batches(name, 0x5EED, 0, nb * n, nb)
+    heat = np.stack([tmc.capi.fx_to_float64(name, bh[b], bh2[b])[0] for b in range(nb)])
+    heat2 = np.stack([tmc.capi.fx_to_float64(name, bh[b], bh2[b])[1] for b in range(nb)])
+    pcg = np.load(GOLD / f"ref_pcg_batches_{name}.npz")
+    gg = heat.reshape(nb, 128, 128).sum(axis=2) if name == "finegrid" else heat
+    zp, okp = batch_means_z(gg, n, pcg["heat"], int(pcg["photons_per_batch"]), min_mean=1e-4)
+    out[f"{name}_vs_unmodified_reference_on_pcg32"] = dict(shells_tested=int(okp.sum()), max_abs_z=float(np.abs(zp[okp]).max()),
+                                                          rms_z=float(np.sqrt((zp[okp] ** 2).mean())), mean_z=float(zp[okp].mean()))
     g = heat.reshape(nb, 128, 128).sum(axis=2) if name == "finegrid" else heat
     z, ok = batch_means_z(g, n, ref["heat"], n_ref, min_mean=1e-4)
     rel_sigma = np.sqrt((g / n).var(axis=0, ddof=1) / nb + (ref["heat"] / n_ref).var(axis=0, ddof=1) / ref["heat"].shape[0])[ok] / (g / n).mean(axis=0)[ok]
