@@ -188,11 +188,16 @@ static uint64_t replay_core(const orc_optics* o, uint32_t rounds, uint64_t seed,
 {
     orc_fx_scales s;
     orc_fx_plan(o, &s);
-    const float spm = (float)(1e4 / (double)o->microns_per_shell / (double)(o->mu_a + o->mu_s));
+    const float spm = (float)(1e4 / (double)o->microns_per_shell / (double)(o->mu_a + o->mu_s));   /* photon.c:9 */
     const uint32_t last = o->shells - 1u;
+    /* positions in units of the grid radius SHELLS / shells_per_mfp: |r| = 1 is the outer edge of the last
+     * shell, so saturating |r|^2 to 1 is the clamp of photon.c:27-29 and shell = trunc(|r| * shell_scale) with
+     * shell_scale the largest float below SHELLS */
+    const float kappa = (float)((double)spm / (double)o->shells);
+    const float shell_scale = nextafterf((float)o->shells, 0.0f);
+    const float radial_step = (float)(-0.693147180559945309417232 * (double)kappa);
     const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
     const uint64_t half = s.heat2_rshift ? ((uint64_t)1 << (s.heat2_rshift - 1)) : 0;
-    const float LN2 = 0.693147182464599609375f;          /* float(ln 2)       */
     const uint32_t FATE_SURVIVE = 429496729u;            /* floor(0.1 * 2^32) */
     static float pol_c[DIR_ENTRIES], pol_s[DIR_ENTRIES], az_cos[DIR_ENTRIES], az_sin[DIR_ENTRIES];
     static int dir_ready = 0;
@@ -239,22 +244,28 @@ static uint64_t replay_core(const orc_optics* o, uint32_t rounds, uint64_t seed,
             /* hop (photon.c:21-24): L = log2(xi), t = -ln2 L; -ln2 is folded into the polar table */
             const float L = log2_xi_of_word(v);
             float rad;
+            const float pc = pol_c[kp] * kappa, ps = pol_s[kp] * kappa;   /* the step in grid-radius units */
+            float r2;
             if (mode == 1) { /* reduced radial walk: x holds the radius, mu = cos(theta_k) */
-                const float t = L * -LN2, tmu = L * pol_c[kp];
-                const float r2 = fmaf(x + x, tmu, fmaf(t, t, x * x));
-                rad = sqrtf(r2 > 0.0f ? r2 : 0.0f);
-                x = rad;
+                const float t = L * radial_step, tmu = L * pc;
+                r2 = fmaf(x + x, tmu, fmaf(t, t, x * x));
             } else {
                 /* spin (photon.c:35-43, sampled directly, BEFORE the hop so that no direction is
                  * carried between events) and move (photon.c:22-24) */
-                const float ts = L * pol_s[kp];
-                x = fmaf(L, pol_c[kp], x);
+                const float ts = L * ps;
+                x = fmaf(L, pc, x);
                 y = fmaf(ts, az_cos[ka], y);
                 z = fmaf(ts, az_sin[ka], z);
-                /* drop (photon.c:26-32) */
-                rad = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+                r2 = fmaf(z, z, fmaf(y, y, x * x));
             }
-            const double sf = floor((double)rad * (double)spm);
+            /* drop (photon.c:26-32): the tally sees |r| clamped to the grid radius, the walk does not */
+            if (mode == 1) {
+                x = sqrtf(r2 > 0.0f ? r2 : 0.0f);
+                rad = x > 1.0f ? 1.0f : x;
+            } else {
+                rad = sqrtf(r2 > 1.0f ? 1.0f : r2);
+            }
+            const double sf = floor((double)rad * (double)shell_scale);
             const uint32_t shell = (sf >= (double)last) ? last : (uint32_t)sf;
             const uint32_t dep = (uint32_t)(((uint64_t)w * s.absorb_q32 + 0x80000000ull) >> 32);
             w -= dep;

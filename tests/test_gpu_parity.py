@@ -159,7 +159,8 @@ def test_result_is_independent_of_split_and_launch_shape(gpu, name, n):
     assert np.array_equal(acc[0], base[0]) and np.array_equal(acc[1], base[1])
     # any block shape / residency / drain interval
     shapes = [dict(block_threads=128), dict(block_threads=512, blocks_per_sm=1), dict(flush_iters=5),
-              dict(block_threads=1024, flush_iters=17)]
+              dict(block_threads=1024, flush_iters=17),
+              dict(tally_layout=1)]    # one histogram per block (integer clamp) instead of per-lane copies (.sat clamp)
     if name == "finegrid":
         shapes = [dict(block_threads=512), dict(flush_iters=64), dict(block_threads=256, flush_iters=100)]
     for opts in shapes:

@@ -509,7 +509,10 @@ int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t fi
     tmc::philox_expand_key(seed, &a.keys);
     a.tallies = d_buf;
     a.counters = d_buf + 2ull * p->shells;
-    a.shells_per_mfp = pl.shells_per_mfp;
+    // positions in units of the grid radius SHELLS / shells_per_mfp (walk_kernel.cuh: radius_sq / shell_bits)
+    a.pos_scale = static_cast<float>(static_cast<double>(pl.shells_per_mfp) / static_cast<double>(p->shells));
+    a.shell_scale = std::nextafterf(static_cast<float>(p->shells), 0.0f);
+    a.radial_step = static_cast<float>(-0.693147180559945309417232 * static_cast<double>(a.pos_scale));
     a.shells = p->shells;
     a.last_bits = tmc::kMagicBits + p->shells - 1u;
     rc = deposit_table(dev, pl, &a.deposits);

@@ -82,7 +82,11 @@ struct WalkArgs {
     const float2* directions;       // global [256] (-ln2 cos, -ln2 sin)(theta_k) | [256] (cos, sin)(phi_k)
     const uint2* deposits;          // global (deposit, rescaled deposit^2) of event e, e = 1 .. last event of gen[n_gen-1]
     uint32_t* queues;               // global scratch: kQueueBytesPerWarp per warp of the grid (survivor queues)
-    float shells_per_mfp;           // reference photon.c:9
+    float pos_scale;                // kappa = shells_per_mfp / SHELLS (photon.c:9): positions are kept in units of the grid
+                                    // radius SHELLS / shells_per_mfp mean free paths, so that |r| = 1 is the outer edge of the
+                                    // last shell and the clamp of photon.c:27-29 becomes the .sat of one FFMA
+    float shell_scale;              // the largest float below SHELLS: trunc(|r| * shell_scale) <= SHELLS-1 for |r| <= 1
+    float radial_step;              // -ln2 * kappa (reduced radial walk only)
     uint32_t shells;                // SHELLS (reference params.h:5)
     uint32_t last_bits;             // 0x4B000000 + SHELLS-1 : clamp in the magic-number domain
     uint32_t flush_blocks;          // Philox blocks (4 events) a warp walks between drains
@@ -243,8 +247,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
 
     {   // stage the direction table (16 copies of every entry) and clear the histograms
         float2* dst = reinterpret_cast<float2*>(table);
-        for (uint32_t i = tid; i < kDirTableBytes / 8u; i += BLOCK)
-            dst[i] = __ldg(a.directions + (i >> 5) + ((i & 16u) ? kDirEntries : 0));
+        for (uint32_t i = tid; i < kDirTableBytes / 8u; i += BLOCK) {
+            float2 d = __ldg(a.directions + (i >> 5) + ((i & 16u) ? kDirEntries : 0));
+            if (!(i & 16u)) {               // polar entries carry the step: scale them to grid-radius units
+                d.x *= a.pos_scale;
+                d.y *= a.pos_scale;
+            }
+            dst[i] = d;
+        }
         for (uint32_t i = tid; i < nwords; i += BLOCK) bins[i] = 0u;
         if (tid == 0u) drain_ticket = 0u;
     }
@@ -289,6 +299,19 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                                                        __shfl_sync(0xffffffffu, ticket, 0) % WARPS, a.check_shift);
     };
 
+    // drop (photon.c:26-29): shell = min(trunc(|r| * shells_per_mfp), SHELLS-1).  Positions are in units of the
+    // grid radius, so |r|^2 saturated to 1 by the .sat of its last FFMA IS the clamp to the overflow bin (every
+    // |r| >= 1 lands in shell SHELLS-1); trunc(|r| * shell_scale) without F2I: add 2^23 rounding toward zero, the
+    // mantissa is the integer.  The one-histogram layout clamps the raw bits instead, to per-lane overflow slots.
+    auto radius_sq = [&](float x, float y, float z) {
+        const float r2 = fmaf(z, z, fmaf(y, y, x * x));
+        return LANE_PRIVATE ? __saturatef(r2) : r2;
+    };
+    auto shell_bits = [&](float rad) {
+        const uint32_t sb = __float_as_uint(__fmaf_rz(rad, a.shell_scale, 8388608.0f));
+        return LANE_PRIVATE ? sb : min(sb, clamp_bits);
+    };
+
     // One scatter event (reference photon.c:21-43) from word S of the current Philox block for
     // every photon of the lane: spin, hop, drop.  `dep` / `dep2` are the warp-uniform deposit
     // (1-albedo) * w and its rescaled square.  Bits of the event word v:
@@ -310,10 +333,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             float rad;
             if constexpr (RADIAL) {
                 // px holds the radius: r'^2 = r^2 + t^2 + 2 r (t mu), >= 0 up to rounding
-                const float t = L * -kLn2, tmu = L * pol.x;
+                const float t = L * a.radial_step, tmu = L * pol.x;
                 const float r2 = fmaf(px[j] + px[j], tmu, fmaf(t, t, px[j] * px[j]));
-                rad = mufu_sqrt(fmaxf(r2, 0.0f));
-                px[j] = rad;
+                px[j] = mufu_sqrt(fmaxf(r2, 0.0f));      // the state keeps the true radius,
+                rad = fminf(px[j], 1.0f);                // the tally sees it clamped to the grid (photon.c:27-29)
             } else {
                 // spin (photon.c:35-43, sampled directly) and move (photon.c:22-24)
                 const float2 azi = lds_f32x2<kSmemTableAbs>(row_offset<0>(v, azimuth_low));
@@ -321,11 +344,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                 px[j] = fmaf(L, pol.x, px[j]);
                 py[j] = fmaf(ts, azi.x, py[j]);
                 pz[j] = fmaf(ts, azi.y, pz[j]);
-                rad = mufu_sqrt(fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j])));
+                rad = mufu_sqrt(radius_sq(px[j], py[j], pz[j]));
             }
-            // drop: shell = min(trunc(|r| * shells_per_mfp), SHELLS-1) (photon.c:26-29) without F2I:
-            // add 2^23 with round-toward-zero, clamp the raw bits, the mantissa is the integer.
-            const uint32_t sb = min(__float_as_uint(__fmaf_rz(rad, a.shells_per_mfp, 8388608.0f)), clamp_bits);
+            const uint32_t sb = shell_bits(rad);
             if constexpr (LANE_PRIVATE) {
                 const uint32_t off = shell_offset(sb, lane_low);
                 if (!PARTIAL || act[j]) {
@@ -414,18 +435,18 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                     for (int j = 0; j < PPL; ++j) {
                         float rad;
                         if constexpr (RADIAL) {
-                            const float t = L[e][j] * -kLn2, tmu = L[e][j] * pol[e][j].x;
+                            const float t = L[e][j] * a.radial_step, tmu = L[e][j] * pol[e][j].x;
                             const float r2 = fmaf(px[j] + px[j], tmu, fmaf(t, t, px[j] * px[j]));
-                            rad = mufu_sqrt(fmaxf(r2, 0.0f));
-                            px[j] = rad;
+                            px[j] = mufu_sqrt(fmaxf(r2, 0.0f));      // the state keeps the true radius,
+                            rad = fminf(px[j], 1.0f);                // the tally sees it clamped to the grid
                         } else {
                             const float ts = L[e][j] * pol[e][j].y;
                             px[j] = fmaf(L[e][j], pol[e][j].x, px[j]);
                             py[j] = fmaf(ts, azi[e][j].x, py[j]);
                             pz[j] = fmaf(ts, azi[e][j].y, pz[j]);
-                            rad = mufu_sqrt(fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j])));
+                            rad = mufu_sqrt(radius_sq(px[j], py[j], pz[j]));
                         }
-                        const uint32_t sb = min(__float_as_uint(__fmaf_rz(rad, a.shells_per_mfp, 8388608.0f)), clamp_bits);
+                        const uint32_t sb = shell_bits(rad);
                         off[e][j] = LANE_PRIVATE ? shell_offset(sb, lane_low) : (sb << 2) + plain_bias;
                     }
             };
@@ -446,7 +467,20 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             look_up(IntTag<0>{});
             if constexpr (G == 4) {
                 walk_group();
-                tally_group();
+                // the four deposits of a full block are 32 contiguous, 32-byte aligned bytes of the table
+                const uint4 d01 = __ldg(reinterpret_cast<const uint4*>(next_deposit));
+                const uint4 d23 = __ldg(reinterpret_cast<const uint4*>(next_deposit) + 1);
+                next_deposit += 4;
+                const uint32_t dp[4] = { d01.x, d01.z, d23.x, d23.z }, dp2[4] = { d01.y, d01.w, d23.y, d23.w };
+#pragma unroll
+                for (int e = 0; e < G; ++e)
+#pragma unroll
+                    for (int j = 0; j < PPL; ++j)
+                        if (!PARTIAL || act[j]) {
+                            red_shared_add<kSmemBinsAbs>(off[e][j], dp[e]);
+                            if constexpr (LANE_PRIVATE) red_shared_add<kSmemBinsAbs + 128u>(off[e][j], dp2[e]);
+                            else red_shared_add<kSmemBinsAbs>(off[e][j] + heat2_off, dp2[e]);
+                        }
             } else if constexpr (G == 2) {
                 walk_group();
                 uint32_t off0[G][PPL];
