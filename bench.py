@@ -7,8 +7,10 @@
 A "step" is one pass of the hot path (reference tiny_mc.c:47-49, i.e. PHOTONS calls of photon())
 over one batch of photons:
   N = 1 : BASELINE.json configs[1] — default optics, 2^26 photons per step on one GPU;
-  N > 1 : BASELINE.json configs[2] — 2^32 photons per step sharded over the N GPUs (the same job at
-          N = 2, 4, 8), one NCCL all-reduce of the 2*SHELLS+4 u64 tally words per step.
+  N > 1 : 2^29 photons per GPU per step (weak scaling; N = 8 is exactly configs[2]: 2^32 photons
+          sharded over 8 GPUs), one NCCL all-reduce of the 2*SHELLS+4 u64 tally words per step.
+          `also` : the other named size of the same N — configs[2] (2^32 photons in total) at N = 2 and 4,
+          the 2^29-photon step at N = 1 (the anchor that makes value_N / (N x anchor) compare equal work).
 There is no input data: the "inputs" are the photon index range and the seed, so nothing has
 to be resident in HBM and nothing is copied host->device; every step simulates a NEW photon range.
 
@@ -171,12 +173,13 @@ def emit(line: dict):
 
 
 # ------------------------------------------------------------------------------ our arm
-NAMED = {   # photons per step: (one GPU, whole job on N > 1 GPUs) and the BASELINE.json config each is
-    "default": ((1 << 26, "BASELINE configs[1]"), (1 << 32, "BASELINE configs[2]")),
+NAMED = {   # photons per step on one GPU (N = 1), photons per GPU per step on N > 1 GPUs (weak scaling)
+    "default": ((1 << 26, "BASELINE configs[1]"), 1 << 29),          # 8 x 2^29 = 2^32 = configs[2]
     # 2^22 photons = 3e10 events per step on one GPU: ~28 cohorts per warp, so the one-cohort tail is ~1 %
-    "highalbedo": ((1 << 22, "BASELINE configs[3] optics, 2^22-photon steps"), (1 << 26, "BASELINE configs[3] optics, 2^26-photon steps")),
-    "finegrid": ((1 << 26, "BASELINE configs[4] optics, 2^26-photon steps"), (1 << 30, "BASELINE configs[4]")),
+    "highalbedo": ((1 << 22, "BASELINE configs[3] optics, 2^22-photon steps"), 1 << 23),
+    "finegrid": ((1 << 26, "BASELINE configs[4] optics, 2^26-photon steps"), 1 << 27),       # 8 x 2^27 = 2^30 = configs[4]
 }
+CONFIGS2_PHOTONS = 1 << 32                      # BASELINE configs[2]: 2^32 photons sharded over 2 / 4 / 8 GPUs
 HASH_SEED, HASH_PHOTONS = 0x5EED, 1 << 26      # the fixed range behind checks.tally_hash at every N
 
 
@@ -222,7 +225,12 @@ def run_ours(args):
 
     cfg = tmc.CONFIGS[args.config]
     shells = cfg["shells"]
-    per_step, named = NAMED[args.config][0 if world == 1 else 1]
+    if world == 1:
+        per_step, named = NAMED[args.config][0]
+    else:
+        per_step = NAMED[args.config][1] * world
+        named = f"weak scaling, {NAMED[args.config][1]} photons per GPU" + (
+            " = BASELINE configs[2]" if args.config == "default" and per_step == CONFIGS2_PHOTONS else "")
     if args.photons_per_gpu:
         per_step, named = args.photons_per_gpu * world, "custom size"
     per_gpu = per_step // world
@@ -242,47 +250,50 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tallies)     # the single collective: 2*SHELLS+4 int64 words, exact
 
-    def device_step(step: int):
-        device_walk(step * per_step, per_step)
-
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident throughput ("value") ----
-    for w in range(args.warmup):
+    def timed_steps(photons_per_step: int, warmup: int, steps: int, first_photon: int):
+        """`warmup` untimed and `steps` timed passes over consecutive photon ranges of `photons_per_step`;
+        returns (device ms of the timed steps, max over ranks; kernels launched in them, all ranks; wall s)."""
+        nonlocal launches
+        for w in range(warmup):
+            tallies.zero_()
+            device_walk(first_photon + w * photons_per_step, photons_per_step)
+        sync_all()
         tallies.zero_()
-        device_step(w)
-    sync_all()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        sync_all()
+        launches = 0
+        wall0 = time.perf_counter()
+        for k in range(steps):
+            flush_buf.fill_(k & 0xFF)       # L2 flush between timed iterations (outside the events)
+            if world > 1:
+                tallies.zero_()              # every rank contributes its own step tallies to the reduce
+            starts[k].record(stream)
+            device_walk(first_photon + (warmup + k) * photons_per_step, photons_per_step)
+            stops[k].record(stream)
+        sync_all()
+        wall_s = time.perf_counter() - wall0
+        ms = sum(s_.elapsed_time(e_) for s_, e_ in zip(starts, stops))
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+        n_launches = launches
+        if world > 1:
+            tl = t.clone()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+            n_launches = int(tl[1].item())
+        return float(t[0].item()), n_launches, wall_s
+
+    # ---- device-resident throughput ("value") ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    tallies.zero_()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    sync_all()
-    launches = 0
-    wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush_buf.fill_(k & 0xFF)       # L2 flush between timed iterations (outside the events)
-        if world > 1:
-            tallies.zero_()              # every rank contributes its own step tallies to the reduce
-        starts[k].record(stream)
-        device_step(args.warmup + k)
-        stops[k].record(stream)
-    sync_all()
-    wall = time.perf_counter() - wall0
-    timed_launches = launches
-    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
-    t = torch.tensor([dev_ms, float(timed_launches)], dtype=torch.float64, device=dev)
-    if world > 1:
-        tl = t.clone()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
-        timed_launches = int(tl[1].item())
-    dev_ms = float(t[0].item())
+    dev_ms, timed_launches, wall = timed_steps(per_step, args.warmup, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
     tmc.device_tallies_check(args.config, local_rank, tallies.data_ptr(), stream.cuda_stream)   # mandatory after photons_device
     host_tallies = tallies.cpu().numpy().astype(np.uint64)
@@ -291,6 +302,18 @@ def run_ours(args):
     photons_counted = int(host_tallies[2 * shells + 1])
     events_per_photon = events_last / max(photons_counted, 1)
     value = per_step * args.steps / (dev_ms * 1e-3)
+
+    # ---- the other named size of this N (default optics): N = 2, 4 also run BASELINE configs[2] (2^32 photons in
+    #      total; at N = 8 the weak-scaling step above IS configs[2]); N = 1 also runs the 2^29-photon step of the
+    #      N > 1 lines, so that value_N / (N x anchor) compares equal per-GPU work ----
+    also = None
+    if args.config == "default" and not args.photons_per_gpu:
+        extra = NAMED["default"][1] if world == 1 else (CONFIGS2_PHOTONS if per_step != CONFIGS2_PHOTONS else 0)
+        if extra:
+            ms_x, _, _ = timed_steps(extra, 1, 3, 1 << 40)
+            also = {"photons_per_step": extra, "value": extra * 3 / (ms_x * 1e-3), "unit": METRIC, "ms_per_step": ms_x / 3, "steps": 3,
+                    "what": ("the 2^29-photon step the N > 1 lines run per GPU (weak-scaling anchor)" if world == 1
+                             else f"BASELINE configs[2]: 2^32 photons per step sharded over {world} GPUs")}
 
     # ---- the same fixed photon range at every N: its tally words must hash the same (north star:
     #      "bit-reproducible across 1/2/4/8 GPUs"; reference loop tiny_mc.c:47-49 sharded) ----
@@ -381,7 +404,7 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f32+u32 (fp32 walk, 32-bit fixed-point weights, u64 tallies)", "data": "synthetic",
         "config": {
@@ -389,8 +412,9 @@ def run_ours(args):
                          f"{cfg['microns_per_shell']} um shells), {per_step} photons per step = {named}, "
                          f"{per_gpu} photons per GPU per step"),
             "parallelism": f"photon-index shards x{world}" + (", one NCCL all-reduce of the tally words per step" if world > 1 else ""),
-            "scaling_note": "N = 1 is configs[1] (2^26 photons); N = 2, 4, 8 all run configs[2] (2^32 photons in total, "
-                            "strong scaling between them)",
+            "scaling_note": "N = 1 is configs[1] (2^26 photons per step); N = 2, 4, 8 run 2^29 photons per GPU per step (weak "
+                            "scaling; N = 8 is exactly configs[2]); `also` carries the other named size of this N: configs[2] "
+                            "(2^32 photons in total) at N = 2 and 4, the 2^29-photon anchor at N = 1",
             "philox_rounds": args.philox_rounds,
             "l2": "flushed between timed steps (256 MB fill); the kernel has no input to cache",
             "blocks": info["blocks_per_gpu"], "threads_per_block": info["threads_per_block"],
@@ -403,6 +427,7 @@ def run_ours(args):
                         "float accumulation; wall clock.  No inputs exist to copy host->device (launch arguments only)",
                 "library_kernel_ms_last_step": info["kernel_ms"], "library_call_ms_last_step": info["call_ms"]},
         "gpu_launches": timed_launches,
+        "also": also,
         "roofline": roofline,
         "checks": {"absorbed_weight_per_photon": absorbed, "tally_range_flag": flag, "wall_ms_per_step": 1e3 * wall / args.steps,
                    "tally_hash": tally_hash, "tally_hash_library_path": lib_hash,

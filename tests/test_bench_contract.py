@@ -53,7 +53,7 @@ def test_gpu_arm_prints_the_contract_keys():
     # ncu capture), not the canonical-budget figure: below 1 by construction, and below the dispatch-slot figure
     assert 0.3 < r["frac"] < 1.0 and r["frac"] < r["frac_dispatch"] < 1.0 and r["frac_canonical_88"] > r["frac"]
     assert r["traffic"] is not None and r["ncu_capture"]["matches_this_run"]
-    assert d["scaling"] == "weak"
+    assert d["scaling"] == "weak" and d["also"]["photons_per_step"] == 1 << 29 and d["also"]["value"] > 1e9
     # the fixed-range tally hash: the torch-stream path and the library's own host path give the same words
     c = d["checks"]
     assert len(c["tally_hash"]) == 16 and c["tally_hash"] == c["tally_hash_library_path"]
