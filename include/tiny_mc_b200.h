@@ -91,7 +91,10 @@ int tmc_abi_version(void);
  * (0 = auto, 1 = one histogram per block, 2 = one per lane), "tally_check_bits" (31; tests lower
  * it to exercise the TMC_ERR_TALLY_RANGE retry), "walk_mode" (0 = the 3-D walk of reference
  * photon.c:20-50; 1 = a reduced radial walk, r'^2 = r^2 + t^2 + 2 r t mu, distribution-identical for
- * this isotropic problem: a cross-check, never the benchmarked path; default block shape only).
+ * this isotropic problem: a cross-check, never the benchmarked path; default block shape only),
+ * "batch_streams" (2 = the launches of tmc_photons_fx_batches alternate between two streams per device so
+ * that one launch's tail overlaps the next, 1 = one stream), "batch_capacity" (tally slots tmc_prepare
+ * sizes the buffers for, so that a later batched call allocates nothing; default 1).
  * 0 restores the default.                                                                     */
 int tmc_set_option(const char* name, long long value);
 

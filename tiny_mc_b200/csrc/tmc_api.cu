@@ -41,7 +41,8 @@ struct Device {
     int id = -1;
     int sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream2 = nullptr;        // odd slots of a batched call: the tail of one launch overlaps the next
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     unsigned long long* d_buf = nullptr;   // u64[2*shells+4]
     size_t buf_words = 0;
     ncclComm_t comm = nullptr;
@@ -66,6 +67,8 @@ struct Options {
     int tally_layout = 0;    // 0 = auto, 1 = plain per-block histogram, 2 = lane-private
     int tally_check_bits = 31;   // a drained u32 word >= 2^bits triggers the retry (tests lower it)
     int walk_mode = 0;           // 0 = the 3-D walk (the product), 1 = the reduced radial walk (cross-check only)
+    int batch_streams = 2;       // streams per device the launches of a batched call alternate between (1 or 2)
+    int batch_capacity = 1;      // tally slots tmc_prepare sizes the device and pinned buffers for
 };
 
 struct Lib {
@@ -416,6 +419,8 @@ double shells_per_mfp_of(const tmc_params* p)
     return 1e4 / static_cast<double>(p->microns_per_shell) / static_cast<double>(p->mu_a + p->mu_s);
 }
 
+double g_launch_us = 0.0;   // host time inside cudaLaunchKernel since the last trace line (TMC_TRACE)
+
 int configure_launch(const tmc_params* p, const Plan& pl, int device_sms, uint64_t count, uint32_t flush_override, LaunchCfg* cfg)
 {
     bool lane_private = p->shells <= tmc::kLanePrivateMaxShells;
@@ -538,7 +543,9 @@ int enqueue_walk(const tmc_params* p, const Plan& pl, uint64_t seed, uint64_t fi
         a.flush_blocks = cfg.flush_iters;
         a.check_shift = static_cast<uint32_t>(g.opt.tally_check_bits);
         void* params[] = { &a };
+        const auto tl0 = std::chrono::steady_clock::now();
         CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(cfg.fn), dim3(cfg.grid), dim3(cfg.block), params, cfg.smem, stream));
+        g_launch_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tl0).count();
         g.info.gpu_launches += 1;
         first += n;
         count -= n;
@@ -622,21 +629,39 @@ int run_slots(const tmc_params* p, const Plan& pl, uint64_t seed, const std::vec
     const size_t words = 2ull * p->shells + 4ull;
     const size_t total = words * slots.size();
     const int ng = static_cast<int>(g.devs.size());
-    int rc = ensure_buffers(total);
+    const size_t capacity = words * static_cast<size_t>(g.opt.batch_capacity);      // growing later costs a (pinned) re-allocation
+    int rc = ensure_buffers(total > capacity ? total : capacity);
     if (rc) return rc;
     LaunchCfg cfg0{};
+    // Slot-major: every device gets its first launch before any device gets its second.  With more than one slot
+    // the launches alternate between two streams per device, so that the blocks of the next launch fill the SMs the
+    // previous one's tail has already left (the walk is one persistent block per SM with a static share of work).
+    const bool two_streams = slots.size() > 1 && g.opt.batch_streams == 2;
     for (int i = 0; i < ng; ++i) {
         Device& d = g.devs[i];
         CUDA_TRY(cudaSetDevice(d.id));
         CUDA_TRY(cudaMemsetAsync(d.d_buf, 0, total * sizeof(unsigned long long), d.stream));
         CUDA_TRY(cudaEventRecord(d.ev0, d.stream));
-        for (size_t k = 0; k < slots.size(); ++k) {
+        if (two_streams) CUDA_TRY(cudaStreamWaitEvent(d.stream2, d.ev0, 0));
+    }
+    for (size_t k = 0; k < slots.size(); ++k)
+        for (int i = 0; i < ng; ++i) {
+            Device& d = g.devs[i];
             const uint64_t count = slots[k].count;
             const uint64_t lo = slots[k].first + count / ng * i + (static_cast<uint64_t>(i) < count % ng ? i : count % ng);
             const uint64_t n = count / ng + (static_cast<uint64_t>(i) < count % ng ? 1 : 0);
             if (n == 0) continue;
-            rc = enqueue_walk(p, pl, seed, lo, n, d.sms, flush_override, d.d_buf + k * words, d.stream, (i == 0 && k == 0) ? &cfg0 : nullptr);
+            CUDA_TRY(cudaSetDevice(d.id));
+            rc = enqueue_walk(p, pl, seed, lo, n, d.sms, flush_override, d.d_buf + k * words, (two_streams && (k & 1u)) ? d.stream2 : d.stream,
+                              (i == 0 && k == 0) ? &cfg0 : nullptr);
             if (rc) return rc;
+        }
+    for (int i = 0; i < ng; ++i) {
+        Device& d = g.devs[i];
+        CUDA_TRY(cudaSetDevice(d.id));
+        if (two_streams) {
+            CUDA_TRY(cudaEventRecord(d.ev2, d.stream2));
+            CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev2, 0));
         }
         CUDA_TRY(cudaEventRecord(d.ev1, d.stream));
     }
@@ -678,8 +703,9 @@ int run_slots(const tmc_params* p, const Plan& pl, uint64_t seed, const std::vec
     g.info.smem_bytes = static_cast<uint32_t>(cfg0.smem);
     if (trace_enabled()) {
         auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
-        std::fprintf(stderr, "tmc trace: %d gpus, %zu slots: enqueue %.0f us, reduce+copy enqueue %.0f us, wait %.0f us (kernels %.0f us), sum %.0f us\n",
-                     ng, slots.size(), us(t0, t1), us(t1, t2), us(t2, t3), worst * 1e3, us(t3, clk::now()));
+        std::fprintf(stderr, "tmc trace: %d gpus, %zu slots: enqueue %.0f us (of which cudaLaunchKernel %.0f us), reduce+copy enqueue %.0f us, wait %.0f us (kernels %.0f us), sum %.0f us\n",
+                     ng, slots.size(), us(t0, t1), g_launch_us, us(t1, t2), us(t2, t3), worst * 1e3, us(t3, clk::now()));
+        g_launch_us = 0.0;
     }
     return TMC_OK;
 }
@@ -827,6 +853,8 @@ int tmc_finalize(void)
         if (d.d_buf) cudaFree(d.d_buf);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.ev2) cudaEventDestroy(d.ev2);
+        if (d.stream2) cudaStreamDestroy(d.stream2);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     g.devs.clear();
@@ -887,8 +915,10 @@ static int init_devices(int n_gpus)
         CUDA_TRY(cudaSetDevice(i));
         CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, i));
         CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreate(&d.ev0));
         CUDA_TRY(cudaEventCreate(&d.ev1));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.ev2, cudaEventDisableTiming));
     }
     if (n_gpus > 1 && g.opt.nccl_reduce) {
         int rc = load_nccl();
@@ -912,7 +942,9 @@ int tmc_prepare(const tmc_params* p)
     const tmc_run_info keep = g.info;
     std::vector<unsigned long long> sum;
     double ms = 0.0;
-    rc = run_range(p, pl, 0x7072657061726521ull, 0, 64ull * g.devs.size(), 0, sum, &ms);   // result discarded
+    // two slots: both streams of every device get their tables, kernel attributes and scratch (result discarded)
+    const uint64_t n = 64ull * g.devs.size();
+    rc = run_slots(p, pl, 0x7072657061726521ull, std::vector<Slot>{ Slot{ 0, n }, Slot{ n, n } }, 0, sum, &ms);
     g.info = keep;
     return rc;
 }
@@ -944,6 +976,14 @@ int tmc_set_option(const char* name, long long value)
     } else if (n == "walk_mode") {
         if (value != 0 && value != 1) return fail(TMC_ERR_BAD_ARG, "walk_mode must be 0 (3-D walk) or 1 (radial cross-check)");
         g.opt.walk_mode = static_cast<int>(value);
+    } else if (n == "batch_streams") {
+        if (value == 0) value = 2;
+        if (value != 1 && value != 2) return fail(TMC_ERR_BAD_ARG, "batch_streams must be 1 or 2");
+        g.opt.batch_streams = static_cast<int>(value);
+    } else if (n == "batch_capacity") {
+        if (value == 0) value = 1;
+        if (value < 1 || value > 4096) return fail(TMC_ERR_BAD_ARG, "batch_capacity must be 1..4096");
+        g.opt.batch_capacity = static_cast<int>(value);
     } else if (n == "tally_layout") {
         if (value < 0 || value > 2) return fail(TMC_ERR_BAD_ARG, "tally_layout must be 0 (auto), 1 (plain) or 2 (lane-private)");
         g.opt.tally_layout = static_cast<int>(value);

@@ -103,12 +103,14 @@ int main(void)
                        MU_S, MU_A, photons);
 
     if (getenv("TMC_NCCL")) tmc_set_option("nccl_reduce", atoi(getenv("TMC_NCCL")));   /* 0: sum the per-GPU words on the host */
+    if (getenv("TMC_BATCH_STREAMS")) tmc_set_option("batch_streams", atoi(getenv("TMC_BATCH_STREAMS")));
     const char* env = getenv("TMC_GPUS");
     if (tmc_init(env ? atoi(env) : 0) != TMC_OK) { /* one-off, outside the timed region */
         fprintf(stderr, "tiny_mc_b200: %s\n", tmc_last_error());
         return 1;
     }
 
+    if (getenv("TMC_JSON")) tmc_set_option("batch_capacity", TMC_BATCHES);   /* buffers for all batches, sized by tmc_prepare */
     if (tmc_prepare(&params) != TMC_OK) { /* tables, buffers, first collective: also outside the timed region */
         fprintf(stderr, "tiny_mc_b200: %s\n", tmc_last_error());
         return 1;

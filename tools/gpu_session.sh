@@ -88,6 +88,13 @@ for l in open("gpurun_out/quick_variants.jsonl"):
     print(f"{d['lib'] or 'in-tree':28s} {d['config']:10s} block {d['block']:4d} x grid {d['grid']:3d} flush {d['flush']:4d}  {d['photons_per_s']:.4g} photons/s  {d['events_per_s']:.4g} events/s")
 PY
   ;;
+batches)   # the batched call (TMC_JSON) against the plain call, C host program, TMC_TRACE timings
+  timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "batches or batch_means" > gpurun_out/pytest_batches.log 2>&1; echo "pytest batches rc=$?"; tail -3 gpurun_out/pytest_batches.log
+  for prog in headless_config2 headless_config3; do
+    TMC_TRACE=1 timeout 300 tiny_mc_b200/bin/$prog 2> gpurun_out/${prog}_plain.err | sed -n 8,9p; grep "tmc trace" gpurun_out/${prog}_plain.err | tail -1
+    TMC_TRACE=1 TMC_JSON=gpurun_out/${prog}.json timeout 300 tiny_mc_b200/bin/$prog 2> gpurun_out/${prog}_json.err | sed -n 8,9p; grep "tmc trace" gpurun_out/${prog}_json.err | tail -1
+    TMC_BATCH_STREAMS=1 TMC_TRACE=1 TMC_JSON=gpurun_out/${prog}.json timeout 300 tiny_mc_b200/bin/$prog 2> gpurun_out/${prog}_json1.err | sed -n 8,9p; grep "tmc trace" gpurun_out/${prog}_json1.err | tail -1
+  done ;;
 quick)
   timeout 600 python tools/quick_bench.py > gpurun_out/quick.jsonl 2> gpurun_out/quick.err; echo "quick rc=$?"; cat gpurun_out/quick.jsonl ;;
 sweep)
