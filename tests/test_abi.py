@@ -75,7 +75,14 @@ def test_argument_validation(tmc):
     assert lib.tmc_set_option(b"philox_rounds", 8) == 2
     assert lib.tmc_set_option(b"no_such_option", 1) == 2
     assert lib.tmc_set_option(b"philox_rounds", 10) == 0
+    for name, good, bad_value in ((b"batch_streams", 1, 3), (b"batch_capacity", 64, 5000), (b"tally_layout", 1, 7)):
+        assert lib.tmc_set_option(name, bad_value) == 2 and lib.tmc_set_option(name, good) == 0 and lib.tmc_set_option(name, 0) == 0
     assert lib.tmc_last_run_info(None) == 2
+    # the batched and the device-checking entry points validate before they touch a device
+    p_ok = tmc.capi.make_params("default")
+    h = np.zeros(101, np.uint64)
+    assert lib.tmc_photons_fx_batches(C.byref(p_ok), 1, 0, 10, 1, None, h.ctypes.data) in (1, 2)     # not initialised / NULL
+    assert lib.tmc_device_tallies_check(None, 0, None, None) == 2
 
 
 @pytest.mark.parametrize("name", ["default", "highalbedo", "finegrid"])
