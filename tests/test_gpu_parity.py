@@ -430,6 +430,19 @@ def test_bad_arguments_on_a_gpu(gpu):
     assert b"shared memory" in lib.tmc_last_error()
 
 
+def test_parameter_sweep_evicts_cached_tables_without_changing_results(gpu):
+    """The per-device deposit-table cache is bounded (16 optics): a sweep over 40 optics evicts the early
+    tables; walking the first optics again rebuilds its table and gives the same words."""
+    first = dict(shells=64, mu_a=1.0, mu_s=10.0, microns_per_shell=100.0)
+    base = gpu.photons_fx(first, 3, 0, 5000)
+    for k in range(40):
+        cfg = dict(shells=64, mu_a=1.0 + 0.05 * (k + 1), mu_s=10.0, microns_per_shell=100.0)
+        h, _ = gpu.photons_fx(cfg, 3, 0, 500)
+        assert gpu.last_run_info().photons == 500 and h.sum() > 0
+    again = gpu.photons_fx(first, 3, 0, 5000)
+    assert np.array_equal(again[0], base[0]) and np.array_equal(again[1], base[1])
+
+
 def test_tally_range_tripwire_retries_then_fails_loudly(gpu):
     """A drained u32 word at or above 2^tally_check_bits makes the host repeat the range with an 8x
     shorter drain interval; if that never helps the call fails with TMC_ERR_TALLY_RANGE instead of

@@ -11,4 +11,8 @@ for name, n in (("default", 20000), ("highalbedo", 200), ("finegrid", 20000)):
     h, h2 = tmc.photons_fx(name, 7, 123, n)
     info = tmc.last_run_info()
     print(name, n, info.events, int(h.sum()), flush=True)
+bh, bh2 = tmc.photons_fx_batches("default", 7, 123, 20000, 5)       # slot-major launches on two streams
+h, h2 = tmc.photons_fx("default", 7, 123, 20000)
+assert (bh.sum(axis=0) == h).all() and (bh2.sum(axis=0) == h2).all()
+print("batches", int(bh.sum()), flush=True)
 tmc.finalize()
