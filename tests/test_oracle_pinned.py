@@ -259,3 +259,25 @@ def test_batch_means_stderr_estimates_the_per_photon_spread(orc):
     assert var_literal[-1] < 0                                  # sqrt -> NaN for the overflow shell
     under = np.sqrt(var_true[:-1] / var_literal[:-1])
     assert under.min() > 1.05 and under.max() < 1.75
+
+
+def test_step_and_direction_bits_are_coupled_only_at_the_1e_minus_4_level(orc):
+    """tmc-stream-4 takes the 8-bit polar index from bits 8..15 of the event word and the 23-bit step from bits
+    9..31: seven bits are shared.  Exact enumeration of all 2^24 (step mantissa, bit 8) pairs: the
+    drift E[t cos(theta)] and the step-weighted anisotropy of the second-moment tensor are what DESIGN.md states."""
+    l = orc.lib()
+    m = np.arange(1 << 23, dtype=np.int64)
+    t = -np.log((m + 0.5) / (1 << 23))
+    drift = second = 0.0
+    for b8 in (0, 1):
+        k = ((m & 127) << 1) | b8                    # bits 8..15 of v = (v >> 8) & 255 with m = v >> 9
+        c = (2 * k + 1) / 256.0 - 1.0
+        drift += (t * c).mean() / 2
+        second += (t * t * c * c).mean() / 2
+    assert abs(drift) < 5e-5                                            # mean free paths per event, along one axis
+    assert abs(second / ((t * t).mean() / 3) - 1.0) < 1e-4              # E[t^2 cos^2] against E[t^2] / 3
+    # the enumeration uses the same bit layout as the replay: spot-check words through the oracle's own mappings
+    for v in (0x00000000, 0x12345678, 0x9ABCDEF0, 0xFFFFFFFF, 0x0000FF00, 0x00010100):
+        mm, kk = v >> 9, (v >> 8) & 255
+        assert abs(l.orc_step_of_word(v) - t[mm]) < 2e-6 * max(1.0, t[mm])
+        assert l.orc_costheta_of_word(v) == (2 * kk + 1) / 256.0 - 1.0 and kk == (((mm & 127) << 1) | ((v >> 8) & 1))
