@@ -223,7 +223,7 @@ constexpr int kPhotonsPerLane = TMC_PPL;   // photons per lane of every compiled
 #define TMC_DEFAULT_BLOCK_PRIVATE 512
 #endif
 #ifndef TMC_DEFAULT_BLOCK_PLAIN
-#define TMC_DEFAULT_BLOCK_PLAIN 1024
+#define TMC_DEFAULT_BLOCK_PLAIN 512
 #endif
 
 // Block shapes: threads per block (two photons per thread) x the residency the register
