@@ -200,6 +200,20 @@ def ncu_facts(config: str):
         return None
 
 
+def mix_ceiling(instr_per_event: float, issue_peak: float, events_per_s: float):
+    """The issue-slot utilisation a B200 SM reaches on the walk's own instruction mix with perfect instruction-level
+    parallelism (tmc_microbench k_walk_mix under ncu, committed in profiles/r02_ncu_facts.json): no pipe is saturated
+    there either; the half-rate ALU-pipe instructions and the two-slot IMAD.WIDE cap the mix at ~69 % of 128 lanes/clk."""
+    path = ROOT / "profiles" / "r02_ncu_facts.json"
+    try:
+        m = json.loads(path.read_text())["_walk_mix_ceiling"]
+    except (OSError, ValueError, KeyError):
+        return None
+    frac = m["issue_active_pct"] / 100.0
+    return {"issue_frac_of_the_mix": frac, "frac_of_mix_ceiling": events_per_s * instr_per_event / issue_peak / frac,
+            "source": "profiles/r02_microbench_walk_mix.md"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -393,6 +407,7 @@ def run_ours(args):
             "frac_dispatch": (events_per_s_per_gpu * facts["dispatch_slots_per_event"] / issue_peak) if facts.get("dispatch_slots_per_event") else None,
             "frac_fma_heavy": facts["fma_heavy_pct"] / 100.0 * events_per_s_per_gpu / ncu_events_per_s,
             "frac_shared_pipe": facts["shared_pipe_pct"] / 100.0 * events_per_s_per_gpu / ncu_events_per_s,
+            "mix_ceiling": mix_ceiling(facts["warp_instr_per_event"], issue_peak, events_per_s_per_gpu),
             "traffic": facts["dram_bytes"],
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full): the path reads no input, HBM is idle",
             "ncu_capture": {"file": "profiles/r02_ncu_facts.json", "report": facts["report"], "block_threads": facts["block_threads"],

@@ -257,6 +257,71 @@ __global__ void __launch_bounds__(kBlock) k_atoms_baseline(Out* out, unsigned se
     if (acc == 0x12345u) out[blockIdx.x].sink = 1;
 }
 
+// The walk's own instruction mix with perfect instruction-level parallelism: per "event" 1 SHF, 1 FADD, 2 MUFU,
+// 3 PRMT, 2 conflict-free LDS.64, 2 FMUL, 6 FFMA, 2 lane-private RED.shared and a quarter of a Philox block
+// (4.5 live IMAD.WIDE + 5 LOP3) = 28.5 instructions, issued for eight independent chains at a time (every
+// instruction's seven neighbours are independent of it), 16 events per loop trip.  No generations, roulette,
+// queues, drains or ragged blocks: what the SM can issue of THIS mix, the ceiling the walk kernel is compared with.
+#define WM_PRMT_A_(i) asm volatile("prmt.b32 %0, %1, %2, 0x5514;" : "=r"(a##i) : "r"(u##i), "r"(lane8));
+#define WM_PRMT_B_(i) asm volatile("prmt.b32 %0, %1, %2, 0x5504;" : "=r"(b##i) : "r"(u##i), "r"(lane8 + 128u));
+#define WM_PRMT_C_(i) asm volatile("prmt.b32 %0, %1, %2, 0x5504;" : "=r"(c##i) : "r"(u##i), "r"(lane4));
+#define WM_LDS_A_(i) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+0x800];" : "=f"(g##i), "=f"(h##i) : "r"(a##i));
+#define WM_LDS_B_(i) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+0x800];" : "=f"(p##i), "=f"(q##i) : "r"(b##i));
+#define WM_FFMA_G_(i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f##i) : "f"(g##i), "f"(h##i));
+#define WM_FFMA_P_(i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f##i) : "f"(p##i), "f"(q##i));
+#define WM_RED_(i) asm volatile("red.shared.add.u32 [%0+0x10800], %1;" ::"r"(c##i), "r"(u##i));
+#define WM_RED2_(i) asm volatile("red.shared.add.u32 [%0+0x10880], %1;" ::"r"(c##i), "r"(u##i));
+#define WM_SHFF_(i) asm volatile("{ .reg .u32 t; shf.r.wrap.b32 t, %1, 0x7f, 9; mov.b32 %0, t; }" : "=f"(e##i) : "r"(u##i));
+#define WM_FADD_E_(i) asm volatile("add.rn.f32 %0, %0, 0fBF7FFFFF;" : "+f"(e##i));
+#define WM_LG2_E_(i) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(e##i));
+#define WM_FMUL_E_(i) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(f##i) : "f"(e##i));
+#define WM_SQRT_(i) asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(f##i));
+// DROP selects what is left out, to see what each instruction class costs inside the mix:
+// 0 nothing, 1 the three PRMT and the SHF (ALU pipe), 2 the Philox quarter block, 3 the shared-memory instructions,
+// 4 the two MUFU, 5 the FP32 arithmetic
+template <int DROP>
+__global__ void __launch_bounds__(512, 1) k_walk_mix(Out* out, unsigned seed)
+{
+    extern __shared__ __align__(16) unsigned wm_smem[];      // [pad to 0x800 | 64 KB table | 64 KB bins: 256 shells x 2 x 32 lanes]
+    const unsigned base = (unsigned)__cvta_generic_to_shared(wm_smem);
+    for (unsigned i = threadIdx.x; i < (0x800u - base + 0x10000u + 0x10000u) / 4u; i += blockDim.x) wm_smem[i] = 0x3F800000u;
+    F_DECL;
+    U_DECL;
+    const unsigned lane8 = (threadIdx.x & 15u) * 8u, lane4 = (threadIdx.x & 31u) * 4u;
+    unsigned a0 = lane8, a1 = lane8, a2 = lane8, a3 = lane8, a4 = lane8, a5 = lane8, a6 = lane8, a7 = lane8;
+    unsigned b0 = lane8 + 128u, b1 = b0, b2 = b0, b3 = b0, b4 = b0, b5 = b0, b6 = b0, b7 = b0;
+    unsigned c0 = lane4, c1 = lane4, c2 = lane4, c3 = lane4, c4 = lane4, c5 = lane4, c6 = lane4, c7 = lane4;
+    float g0 = ca, g1 = ca, g2 = ca, g3 = ca, g4 = ca, g5 = ca, g6 = ca, g7 = ca, h0 = cb, h1 = cb, h2 = cb, h3 = cb, h4 = cb, h5 = cb, h6 = cb, h7 = cb;
+    float p0 = ca, p1 = ca, p2 = ca, p3 = ca, p4 = ca, p5 = ca, p6 = ca, p7 = ca, q0 = cb, q1 = cb, q2 = cb, q3 = cb, q4 = cb, q5 = cb, q6 = cb, q7 = cb;
+    float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f, e4 = 1.5f, e5 = 1.5f, e6 = 1.5f, e7 = 1.5f;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters / 4; ++it) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {      // 8 events each; 4 wide steps in the first half, 5 in the second
+            if (DROP != 1) { REP8(WM_SHFF_) }
+            if (DROP != 5) { REP8(WM_FADD_E_) }
+            if (DROP != 4) { REP8(WM_LG2_E_) }
+            if (DROP != 1) { REP8(WM_PRMT_A_) REP8(WM_PRMT_B_) }
+            if (DROP != 3) { REP8(WM_LDS_A_) REP8(WM_LDS_B_) }
+            if (DROP != 5) { REP8(WM_FMUL_E_) REP8(WM_FFMA_G_) REP8(WM_FFMA_P_) REP8(FFMA_) REP8(FMUL_) REP8(FFMA_) REP8(FFMA_) }
+            if (DROP != 4) { REP8(WM_SQRT_) }
+            if (DROP != 5) { REP8(FFMA_) }
+            if (DROP != 1) { REP8(WM_PRMT_C_) }
+            if (DROP != 3) { REP8(WM_RED_) REP8(WM_RED2_) }
+            if (DROP != 2) {
+                REP8(WIDE_STEP_) REP8(WIDE_STEP_) REP8(WIDE_STEP_) REP8(WIDE_STEP_)
+                if (half == 0) { REP8(EXTRA_LOP_) } else { REP8(WIDE_STEP_) }
+            }
+        }
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x].cycles = t1 - t0;
+    if ((F_SINK ^ U_SINK ^ a0 ^ b0 ^ c0 ^ __float_as_uint(e0 + g0 + h0 + p0 + q0)) == 0x12345u) out[blockIdx.x].sink = 1;
+}
+
 struct Result {
     double cycles, ms;
 };
@@ -345,7 +410,25 @@ int main(int argc, char** argv)
     SIMPLE(k_mix_14ffma_2mufu, 18);
     SIMPLE(k_mix_8ffma_8lop3_2mufu, 18);
     SIMPLE(k_philox10, 80);     // 2 x (20 IMAD.WIDE + 20 LOP3), key schedule folded by ptxas
-
+    {   // the walk's instruction mix, 16 warps per SM like the shipped kernel (one 512-thread block per SM, 130 KB)
+        const size_t wm_bytes = 0x800 + 0x10000 + 0x10000;
+        auto mix = [&](const char* name, auto kernel, double inst_per_trip) {
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wm_bytes));
+            Result r = run([&] { kernel<<<sms, 512, wm_bytes>>>(d_out, 1u); }, d_out, sms);
+            const double winst = inst_per_trip * (kIters / 4) * 16.0;
+            printf("{\"test\": \"%s\", \"warp_inst_per_clk_per_sm\": %.3f, \"cycles\": %.0f, \"ms\": %.4f, \"sm_mhz\": %.0f, \"warps_per_sm\": 16, "
+                   "\"instructions_per_event\": %.2f, \"cycles_per_event_per_smsp\": %.2f}\n",
+                   name, winst / r.cycles, r.cycles, r.ms, r.cycles / r.ms * 1e-3, inst_per_trip / 16.0, r.cycles / ((kIters / 4) * 16.0 * 4.0));
+            fflush(stdout);
+        };
+        // per trip of 16 events: 19 walk instructions + a quarter Philox block (4.5 IMAD.WIDE + 5 LOP3) each = 456
+        mix("k_walk_mix", k_walk_mix<0>, 456.0);
+        mix("k_walk_mix_no_prmt_shf", k_walk_mix<1>, 456.0 - 64.0);
+        mix("k_walk_mix_no_philox", k_walk_mix<2>, 456.0 - 152.0);
+        mix("k_walk_mix_no_shared", k_walk_mix<3>, 456.0 - 64.0);
+        mix("k_walk_mix_no_mufu", k_walk_mix<4>, 456.0 - 32.0);
+        mix("k_walk_mix_no_fp32", k_walk_mix<5>, 456.0 - 144.0);
+    }
     const int nbs[] = {101, 1024, 8192};
     for (int nb : nbs) {
         const size_t sm = (nb + 32) * sizeof(unsigned);

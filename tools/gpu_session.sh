@@ -95,6 +95,9 @@ batches)   # the batched call (TMC_JSON) against the plain call, C host program,
     TMC_TRACE=1 TMC_JSON=gpurun_out/${prog}.json timeout 300 tiny_mc_b200/bin/$prog 2> gpurun_out/${prog}_json.err | sed -n 8,9p; grep "tmc trace" gpurun_out/${prog}_json.err | tail -1
     TMC_BATCH_STREAMS=1 TMC_TRACE=1 TMC_JSON=gpurun_out/${prog}.json timeout 300 tiny_mc_b200/bin/$prog 2> gpurun_out/${prog}_json1.err | sed -n 8,9p; grep "tmc trace" gpurun_out/${prog}_json1.err | tail -1
   done ;;
+mixncu)   # the walk-mix ceiling micro-benchmark alone, with ncu's pipe counters
+  timeout 300 ncu --metrics sm__cycles_elapsed.avg,smsp__inst_executed.sum,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,sm__issue_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio,smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio \
+      --clock-control none -k regex:k_walk_mix --csv --log-file gpurun_out/mix_ncu.csv tiny_mc_b200/bin/tmc_microbench > gpurun_out/mix_under_ncu.jsonl 2>&1; echo "mixncu rc=$?"; grep -E "k_walk_mix" gpurun_out/mix_ncu.csv | awk -F'","' '{print $(NF-2), $(NF-1), $NF}' | tail -14 ;;
 quick)
   timeout 600 python tools/quick_bench.py > gpurun_out/quick.jsonl 2> gpurun_out/quick.err; echo "quick rc=$?"; cat gpurun_out/quick.jsonl ;;
 sweep)
