@@ -20,6 +20,8 @@ only — the fixtures are what travels to the GPU box and into git).
   *_pershell_finegrid.npz  config 5 at its native 5 um resolution: per-shell mean and batch-means
                            variance of the mean (256 batches of 2^19 photons), all 16384 shells,
                            from the xoshiro port and from the unmodified reference on PCG32.
+  *_batches_default_1e9.npz  default optics at 64 x 2^24 = 1.07e9 photons per reference (unmodified reference on
+                           PCG32, port on xoshiro256**): per-shell precision 0.01 %.  Opt-in: `make_golden.py default_1e9`.
   headless_asshipped.txt   stdout of the reference `headless` built exactly as its Makefile does,
                            SEED=20141017; with ref_float_tallies.json["headless"] (same seed, same
                            32768 photons) it pins the printout formatter byte for byte.
@@ -103,6 +105,14 @@ def main():
         np.savez_compressed(GOLD / f"ref_pcg_batches_{name}.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
                             photons_per_batch=n, chunk=chunk)
         print(f"{name} (unmodified reference on pcg32): total/photon {heat.sum() / (nb * n):.6f}, wall {wall:.1f} s")
+    if "default_1e9" in only:      # opt-in (25 minutes on 8 cores): default optics at 1.07e9 photons per reference
+        nb, n = 64, 1 << 24
+        seeds = [70000 + 13 * b for b in range(nb)]
+        for tag, kw in (("ref_pcg", dict(impl="reference_pcg")), ("port_xoshiro", dict(impl="port", rng="xoshiro"))):
+            heat, heat2, _, secs, wall = orc.run_batches("default", seeds, n, chunk=256, **kw)
+            np.savez_compressed(GOLD / f"{tag}_batches_default_1e9.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
+                                photons_per_batch=n, chunk=256)
+            print(f"default 1e9 ({tag}): total/photon {heat.sum() / (nb * n):.7f}, wall {wall:.1f} s")
     if not only or "finegrid_pershell" in only:
         # config 5 per 5 um shell: mean and variance of the mean from 256 batches of 2^19 photons
         nb, n = 256, 1 << 19

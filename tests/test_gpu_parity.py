@@ -307,6 +307,24 @@ def test_sound_generator_fixtures_agree_with_the_gpu_and_libc_does_not(gpu):
     assert np.abs(z).max() > 4.0
 
 
+@pytest.mark.parametrize("fixture", ["ref_pcg", "port_xoshiro"])
+def test_default_optics_against_1e9_reference_photons(gpu, fixture):
+    """The same 4-sigma bar an order of magnitude deeper: 4.3e9 GPU photons (64 batches of 2^26, one batched call)
+    against 1.07e9 photons of the unmodified reference on PCG32 / of the port on xoshiro256**: the per-shell
+    standard error is 0.01 % of the shell's heat, the level at which 8-bit direction tables, the 23-bit step or the
+    shared step / direction bits of tmc-stream-4 would have to show if they mattered."""
+    ref = np.load(GOLDEN / f"{fixture}_batches_default_1e9.npz")
+    nb, n = 64, 1 << 26
+    bh, bh2 = gpu.photons_fx_batches("default", 0xD1CE, 0, nb * n, nb)
+    heat = np.stack([gpu.capi.fx_to_float64("default", bh[b], bh2[b])[0] for b in range(nb)])
+    z, ok = batch_means_z(heat, n, ref["heat"], int(ref["photons_per_batch"]))
+    assert ok.all()
+    assert np.abs(z).max() < 4.0, (np.abs(z).argmax(), z)
+    assert abs(z.mean()) < 0.6 and np.sqrt((z ** 2).mean()) < 1.4
+    tot_gpu, tot_ref = heat.sum() / (nb * n), ref["heat"].sum() / (ref["heat"].shape[0] * int(ref["photons_per_batch"]))
+    assert abs(tot_gpu - tot_ref) < 2e-5
+
+
 def test_literal_contract_against_the_unmodified_reference(gpu):
     """Against the UNMODIFIED reference object code on libc rand() at a scale comparable with
     the one it ships with (PHOTONS = 32768, reference params.h:10): one 65536-photon reference

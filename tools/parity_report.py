@@ -31,6 +31,21 @@ for fixture in ("ref_pcg", "port_xoshiro"):
         max_abs_z=float(np.abs(z).max()), rms_z=float(np.sqrt((z ** 2).mean())), mean_z=float(z.mean()),
         shells_beyond_3_sigma=int((np.abs(z) > 3).sum()), mean_z_per_100_shells=[round(float(v), 2) for v in trend],
         median_relative_sigma_per_shell=float(np.median(np.sqrt(var + ref["var_of_mean"])[ok] / mean[ok])))
+# default optics against the 1.07e9-photon references (4.3e9 GPU photons)
+nb, n = 64, 1 << 26
+bh, bh2 = tmc.photons_fx_batches("default", 0xD1CE, 0, nb * n, nb)
+heat9 = np.stack([tmc.capi.fx_to_float64("default", bh[b], bh2[b])[0] for b in range(nb)])
+for fixture in ("ref_pcg", "port_xoshiro"):
+    ref = np.load(GOLD / f"{fixture}_batches_default_1e9.npz")
+    n_ref = int(ref["photons_per_batch"])
+    z, ok = batch_means_z(heat9, n, ref["heat"], n_ref)
+    rel = np.sqrt((heat9 / n).var(axis=0, ddof=1) / nb + (ref["heat"] / n_ref).var(axis=0, ddof=1) / ref["heat"].shape[0]) / (heat9 / n).mean(axis=0)
+    out[f"default_1e9_vs_{fixture}"] = dict(gpu_photons=nb * n, reference_photons=ref["heat"].shape[0] * n_ref, shells_tested=int(ok.sum()),
+                                            max_abs_z=float(np.abs(z).max()), rms_z=float(np.sqrt((z ** 2).mean())), mean_z=float(z.mean()),
+                                            shells_beyond_3_sigma=int((np.abs(z) > 3).sum()), median_relative_sigma_per_shell=float(np.median(rel)),
+                                            absorbed_per_photon_gpu=float(heat9.sum() / (nb * n)),
+                                            absorbed_per_photon_reference=float(ref["heat"].sum() / (ref["heat"].shape[0] * n_ref)),
+                                            z=[round(float(v), 2) for v in z])
 for name, nb, n in (("default", 64, 1 << 22), ("highalbedo", 64, 1 << 15), ("finegrid", 64, 1 << 22)):
     ref = np.load(GOLD / f"port_xoshiro_batches_{name}.npz")
     n_ref = int(ref["photons_per_batch"])
