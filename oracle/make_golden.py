@@ -113,6 +113,16 @@ def main():
             np.savez_compressed(GOLD / f"{tag}_batches_default_1e9.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
                                 photons_per_batch=n, chunk=256)
             print(f"default 1e9 ({tag}): total/photon {heat.sum() / (nb * n):.7f}, wall {wall:.1f} s")
+    if "finegrid_pershell_1e9" in only:      # opt-in (20 minutes on 8 cores): config 5 per 5 um shell at 1.07e9 photons per reference
+        nb, n = 256, 1 << 22
+        seeds = [90000 + 17 * b for b in range(nb)]
+        for tag, kw in (("ref_pcg", dict(impl="reference_pcg")), ("port_xoshiro", dict(impl="port", rng="xoshiro"))):
+            heat, heat2, _, secs, wall = orc.run_batches("finegrid", seeds, n, chunk=256, **kw)
+            per = heat / n
+            np.savez_compressed(GOLD / f"{tag}_pershell_finegrid_1e9.npz", mean=per.mean(axis=0),
+                                var_of_mean=per.var(axis=0, ddof=1) / nb, heat2_mean=(heat2 / n).mean(axis=0),
+                                batches=nb, photons_per_batch=n, seeds=np.array(seeds))
+            print(f"finegrid per shell 1e9 ({tag}): total/photon {per.sum(axis=1).mean():.7f}, wall {wall:.1f} s")
     if not only or "finegrid_pershell" in only:
         # config 5 per 5 um shell: mean and variance of the mean from 256 batches of 2^19 photons
         nb, n = 256, 1 << 19

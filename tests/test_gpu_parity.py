@@ -271,6 +271,26 @@ def test_every_shell_within_4_sigma_of_the_reference_walk(gpu, name, nb, n):
 
 
 @pytest.mark.parametrize("fixture", ["ref_pcg", "port_xoshiro"])
+def test_config5_every_5um_shell_against_1e9_reference_photons(gpu, fixture):
+    """Config 5 per 5 um shell an order of magnitude deeper: 4.3e9 GPU photons (256 batches of 2^24, one batched
+    call) against 1.07e9 reference photons; per-shell standard error ~0.03 % where the shells are populated."""
+    ref = np.load(GOLDEN / f"{fixture}_pershell_finegrid_1e9.npz")
+    nb, n = 256, 1 << 24
+    bh, _ = gpu.photons_fx_batches("finegrid", 0xF1E9, 0, nb * n, nb)
+    s1 = 2.0 ** -int(gpu.fx_scales("finegrid").heat_shift)
+    per = bh.astype(np.float64) * (s1 / n)
+    mean, var = per.mean(axis=0), per.var(axis=0, ddof=1) / nb
+    ok = np.maximum(mean, ref["mean"]) >= 1e-5
+    assert ok.sum() > 1400
+    z = (mean - ref["mean"])[ok] / np.sqrt(var + ref["var_of_mean"])[ok]
+    assert np.abs(z).max() < 4.0, (np.abs(z).argmax(), np.abs(z).max())
+    assert abs(np.sqrt((z ** 2).mean()) - 1.0) < 0.1 and abs(z.mean()) < 0.25
+    assert (np.abs(z) > 3.0).sum() <= 12
+    trend = z[: len(z) // 100 * 100].reshape(-1, 100).mean(axis=1)
+    assert np.abs(trend).max() < 0.5, trend
+
+
+@pytest.mark.parametrize("fixture", ["ref_pcg", "port_xoshiro"])
 def test_config5_every_5um_shell_within_4_sigma(gpu, fixture):
     """Config 5 at its NATIVE resolution (SHELLS=16384, 5 um: 90.9 shells per mean free path — where a
     23-bit step, 8-bit polar and 8-bit azimuth stream would show first): every shell carrying at least

@@ -31,6 +31,21 @@ for fixture in ("ref_pcg", "port_xoshiro"):
         max_abs_z=float(np.abs(z).max()), rms_z=float(np.sqrt((z ** 2).mean())), mean_z=float(z.mean()),
         shells_beyond_3_sigma=int((np.abs(z) > 3).sum()), mean_z_per_100_shells=[round(float(v), 2) for v in trend],
         median_relative_sigma_per_shell=float(np.median(np.sqrt(var + ref["var_of_mean"])[ok] / mean[ok])))
+# config 5 per 5 um shell against the 1.07e9-photon references (4.3e9 GPU photons in 256 batches)
+nb, n = 256, 1 << 24
+bh, _ = tmc.photons_fx_batches("finegrid", 0xF1E9, 0, nb * n, nb)
+per = bh.astype(np.float64) * (2.0 ** -int(tmc.fx_scales("finegrid").heat_shift) / n)
+mean, var = per.mean(axis=0), per.var(axis=0, ddof=1) / nb
+for fixture in ("ref_pcg", "port_xoshiro"):
+    ref = np.load(GOLD / f"{fixture}_pershell_finegrid_1e9.npz")
+    ok = np.maximum(mean, ref["mean"]) >= 1e-5
+    z = (mean - ref["mean"])[ok] / np.sqrt(var + ref["var_of_mean"])[ok]
+    trend = z[: len(z) // 100 * 100].reshape(-1, 100).mean(axis=1)
+    out[f"finegrid_per_shell_1e9_vs_{fixture}"] = dict(
+        gpu_photons=nb * n, reference_photons=int(ref["batches"]) * int(ref["photons_per_batch"]), shells_tested=int(ok.sum()),
+        max_abs_z=float(np.abs(z).max()), rms_z=float(np.sqrt((z ** 2).mean())), mean_z=float(z.mean()),
+        shells_beyond_3_sigma=int((np.abs(z) > 3).sum()), mean_z_per_100_shells=[round(float(v), 2) for v in trend],
+        median_relative_sigma_per_shell=float(np.median(np.sqrt(var + ref["var_of_mean"])[ok] / mean[ok])))
 # default optics against the 1.07e9-photon references (4.3e9 GPU photons)
 nb, n = 64, 1 << 26
 bh, bh2 = tmc.photons_fx_batches("default", 0xD1CE, 0, nb * n, nb)
