@@ -22,6 +22,8 @@ only — the fixtures are what travels to the GPU box and into git).
                            from the xoshiro port and from the unmodified reference on PCG32.
   *_batches_default_1e9.npz  default optics at 64 x 2^24 = 1.07e9 photons per reference (unmodified reference on
                            PCG32, port on xoshiro256**): per-shell precision 0.01 %.  Opt-in: `make_golden.py default_1e9`.
+  *_pershell_finegrid_1e9.npz  config 5 per 5 um shell at 256 x 2^22 = 1.07e9 photons per reference.  Opt-in:
+                           `make_golden.py finegrid_pershell_1e9` (20 minutes on 8 cores).
   headless_asshipped.txt   stdout of the reference `headless` built exactly as its Makefile does,
                            SEED=20141017; with ref_float_tallies.json["headless"] (same seed, same
                            32768 photons) it pins the printout formatter byte for byte.
