@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     uint32_t* const bins = table + kDirTableBytes / 4u;
     const uint32_t plain_bins = a.shells + 31u;                              // per kind, plain layout
     const uint32_t nwords = LANE_PRIVATE ? a.shells * 64u : 2u * plain_bins;
-    // this warp's survivor queues: [generation 1|2][field][kQueueCap], in global memory (a few
+    // this warp's survivor queues: [generation 1|2]{uint4 (x, y, z, photon offset)[kQueueCap], fate[kQueueCap]}, in global memory (a few
     // accesses per cohort; L2-resident), so that shared memory holds only the table and tallies
     uint32_t* const queue = a.queues + static_cast<size_t>(blockIdx.x * WARPS + wid) * (kQueueBytesPerWarp / 4u);
 
@@ -601,6 +601,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             }
             cohort += total_warps;
         } else {                            // a cohort of parked survivors of generation g
+            // one generation's queue: uint4 (x, y, z, photon offset)[kQueueCap], then the fate words
             const uint32_t* q = queue + (g - 1u) * (kQueueFields * kQueueCap);
             const uint32_t start = nq[g - 1u] - take;
             __syncwarp();
@@ -609,10 +610,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                 const uint32_t e = lane * PPL + j;
                 act[j] = e < take;
                 const uint32_t at = act[j] ? start + e : 0u;
-                px[j] = __uint_as_float(q[0u * kQueueCap + at]);
-                py[j] = __uint_as_float(q[1u * kQueueCap + at]);
-                pz[j] = __uint_as_float(q[2u * kQueueCap + at]);
-                rel[j] = q[3u * kQueueCap + at];
+                const uint4 e4 = reinterpret_cast<const uint4*>(q)[at];
+                px[j] = __uint_as_float(e4.x);
+                py[j] = __uint_as_float(e4.y);
+                pz[j] = __uint_as_float(e4.z);
+                rel[j] = e4.w;
                 fate[j] = q[4u * kQueueCap + at];
             }
             __syncwarp();
@@ -631,10 +633,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                     const uint32_t m = __ballot_sync(0xffffffffu, surv[j]);
                     const uint32_t at = nq[g] + __popc(m & lanemask_lt());
                     if (surv[j]) {
-                        q[0u * kQueueCap + at] = __float_as_uint(px[j]);
-                        q[1u * kQueueCap + at] = __float_as_uint(py[j]);
-                        q[2u * kQueueCap + at] = __float_as_uint(pz[j]);
-                        q[3u * kQueueCap + at] = rel[j];
+                        reinterpret_cast<uint4*>(q)[at] = make_uint4(__float_as_uint(px[j]), __float_as_uint(py[j]), __float_as_uint(pz[j]), rel[j]);
                         q[4u * kQueueCap + at] = fate[j];
                     }
                     nq[g] += __popc(m);
