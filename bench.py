@@ -243,8 +243,8 @@ def run_ours(args):
         per_step, named = NAMED[args.config][0]
     else:
         per_step = NAMED[args.config][1] * world
-        named = f"weak scaling, {NAMED[args.config][1]} photons per GPU" + (
-            " = BASELINE configs[2]" if args.config == "default" and per_step == CONFIGS2_PHOTONS else "")
+        named = ("BASELINE configs[2]" if args.config == "default" and per_step == CONFIGS2_PHOTONS
+                 else "weak-scaling step of BASELINE configs[2]: the per-GPU share of its 8-GPU run")
     if args.photons_per_gpu:
         per_step, named = args.photons_per_gpu * world, "custom size"
     per_gpu = per_step // world
@@ -424,7 +424,7 @@ def run_ours(args):
         "dtype": "f32+u32 (fp32 walk, 32-bit fixed-point weights, u64 tallies)", "data": "synthetic",
         "config": {
             "workload": (f"{args.config} optics (SHELLS={shells}, MU_A={cfg['mu_a']}, MU_S={cfg['mu_s']}, "
-                         f"{cfg['microns_per_shell']} um shells), {per_step} photons per step = {named}, "
+                         f"{cfg['microns_per_shell']} um shells), {per_step} photons per step ({named}), "
                          f"{per_gpu} photons per GPU per step"),
             "parallelism": f"photon-index shards x{world}" + (", one NCCL all-reduce of the tally words per step" if world > 1 else ""),
             "scaling_note": "N = 1 is configs[1] (2^26 photons per step); N = 2, 4, 8 run 2^29 photons per GPU per step (weak "
