@@ -243,8 +243,12 @@ def run_ours(args):
         per_step, named = NAMED[args.config][0]
     else:
         per_step = NAMED[args.config][1] * world
-        named = ("BASELINE configs[2]" if args.config == "default" and per_step == CONFIGS2_PHOTONS
-                 else "weak-scaling step of BASELINE configs[2]: the per-GPU share of its 8-GPU run")
+        if args.config != "default":
+            named = f"weak scaling at {NAMED[args.config][1]} photons per GPU"
+        elif per_step == CONFIGS2_PHOTONS:
+            named = "BASELINE configs[2]"
+        else:
+            named = "weak-scaling step of BASELINE configs[2]: the per-GPU share of its 8-GPU run"
     if args.photons_per_gpu:
         per_step, named = args.photons_per_gpu * world, "custom size"
     per_gpu = per_step // world
