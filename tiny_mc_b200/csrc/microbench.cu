@@ -322,6 +322,42 @@ __global__ void __launch_bounds__(512, 1) k_walk_mix(Out* out, unsigned seed)
     if ((F_SINK ^ U_SINK ^ a0 ^ b0 ^ c0 ^ __float_as_uint(e0 + g0 + h0 + p0 + q0)) == 0x12345u) out[blockIdx.x].sink = 1;
 }
 
+// The same mix at twice the occupancy: four chains per thread (so that 64 registers suffice), two 512-thread blocks
+// per SM = 32 warps per SM, bins of 128 shells (97 KB per block).  Does the ceiling of the mix rise with more warps?
+__global__ void __launch_bounds__(512, 2) k_walk_mix_32warps(Out* out, unsigned seed)
+{
+    extern __shared__ __align__(16) unsigned wm_smem[];      // [pad to 0x800 | 64 KB table | 32 KB bins: 128 shells x 2 x 32 lanes]
+    const unsigned base = (unsigned)__cvta_generic_to_shared(wm_smem);
+    for (unsigned i = threadIdx.x; i < (0x800u - base + 0x10000u + 0x8000u) / 4u; i += blockDim.x) wm_smem[i] = 0x3F800000u;
+    float f0 = seed * 1e-9f + threadIdx.x, f1 = f0 + 1, f2 = f0 + 2, f3 = f0 + 3;
+    const float ca = 1.0001f + seed * 1e-12f, cb = 0.5f;
+    unsigned u0 = seed + threadIdx.x, u1 = u0 * 3 + 1, u2 = u0 * 5 + 2, u3 = u0 * 7 + 3;
+    const unsigned ka = seed | 0xD2511F53u, kb = seed ^ 0x9E3779B9u;
+    const unsigned lane8 = (threadIdx.x & 15u) * 8u, lane4 = (threadIdx.x & 31u) * 4u;
+    unsigned a0 = lane8, a1 = lane8, a2 = lane8, a3 = lane8, b0 = lane8 + 128u, b1 = b0, b2 = b0, b3 = b0, c0 = lane4, c1 = lane4, c2 = lane4, c3 = lane4;
+    float g0 = ca, g1 = ca, g2 = ca, g3 = ca, h0 = cb, h1 = cb, h2 = cb, h3 = cb, p0 = ca, p1 = ca, p2 = ca, p3 = ca, q0 = cb, q1 = cb, q2 = cb, q3 = cb;
+    float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f;
+    (void)ka;
+#define WM_PRMT_C7_(i) asm volatile("{ .reg .u32 t; and.b32 t, %1, 0x7f; prmt.b32 %0, t, %2, 0x5504; }" : "=r"(c##i) : "r"(u##i), "r"(lane4));
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters / 4; ++it) {
+#pragma unroll
+        for (int quarter = 0; quarter < 4; ++quarter) {      // 4 events each; 4 or 5 wide steps alternately
+            REP4(WM_SHFF_) REP4(WM_FADD_E_) REP4(WM_LG2_E_) REP4(WM_PRMT_A_) REP4(WM_PRMT_B_) REP4(WM_LDS_A_) REP4(WM_LDS_B_)
+            REP4(WM_FMUL_E_) REP4(WM_FFMA_G_) REP4(WM_FFMA_P_) REP4(FFMA_) REP4(FMUL_) REP4(FFMA_) REP4(FFMA_) REP4(WM_SQRT_) REP4(FFMA_)
+            REP4(WM_PRMT_C7_) REP4(WM_RED_) REP4(WM_RED2_)
+            REP4(WIDE_STEP_) REP4(WIDE_STEP_) REP4(WIDE_STEP_) REP4(WIDE_STEP_)
+            if (quarter & 1) { REP4(WIDE_STEP_) }
+        }
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x].cycles = t1 - t0;
+    if ((__float_as_uint(f0 + f1 + f2 + f3 + e0 + g0 + h0 + p0 + q0) ^ u0 ^ u1 ^ u2 ^ u3 ^ a0 ^ b0 ^ c0) == 0x12345u) out[blockIdx.x].sink = 1;
+}
+
 struct Result {
     double cycles, ms;
 };
@@ -428,6 +464,14 @@ int main(int argc, char** argv)
         mix("k_walk_mix_no_shared", k_walk_mix<3>, 456.0 - 64.0);
         mix("k_walk_mix_no_mufu", k_walk_mix<4>, 456.0 - 32.0);
         mix("k_walk_mix_no_fp32", k_walk_mix<5>, 456.0 - 144.0);
+        {   // 32 warps per SM: two blocks per SM, four chains per thread (one extra LOP3 per event for the 7-bit shell mask)
+            const size_t b2 = 0x800 + 0x10000 + 0x8000;
+            CK(cudaFuncSetAttribute(k_walk_mix_32warps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2));
+            Result r = run([&] { k_walk_mix_32warps<<<2 * sms, 512, b2>>>(d_out, 1u); }, d_out, sms);
+            printf("{\"test\": \"k_walk_mix_32warps\", \"cycles\": %.0f, \"ms\": %.4f, \"warps_per_sm\": 32, \"cycles_per_event_per_smsp\": %.2f}\n",
+                   r.cycles, r.ms, r.cycles / ((kIters / 4) * 16.0 * 8.0));
+            fflush(stdout);
+        }
     }
     const int nbs[] = {101, 1024, 8192};
     for (int nb : nbs) {
