@@ -213,9 +213,6 @@ int deposit_table(int device, const Plan& pl, const uint2** out)
 }
 
 using KernelFn = void (*)(const WalkArgs);
-#ifndef TMC_PPL
-#define TMC_PPL 2
-#endif
 constexpr int kPhotonsPerLane = TMC_PPL;   // photons per lane of every compiled kernel variant
 
 // default block shapes (measured best, profiles/): lane-private tallies / one histogram per block
@@ -232,6 +229,9 @@ constexpr int kPhotonsPerLane = TMC_PPL;   // photons per lane of every compiled
 template <int ROUNDS, bool LANE_PRIVATE>
 KernelFn kernel_for_block(int block, int per_sm)
 {
+#ifdef TMC_ONLY_BLOCK   /* timing-experiment builds (tools/experiments.sh): one block shape, one block per SM */
+    return block == TMC_ONLY_BLOCK && per_sm == 1 ? tmc::photon_walk_kernel<ROUNDS, TMC_ONLY_BLOCK, 1, LANE_PRIVATE, false, kPhotonsPerLane> : nullptr;
+#else
     // (threads per block, blocks per SM the register budget is compiled for)
     switch (block * 8 + per_sm) {
     case 128 * 8 + 3: return tmc::photon_walk_kernel<ROUNDS, 128, 3, LANE_PRIVATE, false, kPhotonsPerLane>;   // 168 registers
@@ -242,6 +242,7 @@ KernelFn kernel_for_block(int block, int per_sm)
     case 1024 * 8 + 1: return tmc::photon_walk_kernel<ROUNDS, 1024, 1, LANE_PRIVATE, false, kPhotonsPerLane>; //  64
     default: return nullptr;
     }
+#endif
 }
 
 // the reduced radial walk ("walk_mode" = 1) is compiled for the default shapes only

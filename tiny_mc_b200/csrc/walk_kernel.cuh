@@ -30,7 +30,9 @@
 //    tallies => the result does not depend on thread/block/GPU count or on atomic ordering.
 //    Grids too fine for per-lane copies use one u32 histogram per block plus 32 per-lane
 //    slots for the overflow bin.
-//  * Per event and photon: 2 MUFU (lg2 for the step, sqrt for the radius), 10 FP32 operations,
+//  * Per event and photon: 2 MUFU (lg2 for the step, sqrt for the radius), 10 FP32 operations
+//    in 8 instructions (the (y, z) update is one FFMA2, xi and the shell number of the lane's two
+//    photons come out of one FADD2 / FFMA2.RZ: Blackwell's packed f32x2, TMC_PACKED),
 //    2 shared atomics, two conflict-free LDS.64 for the direction (polar and azimuth tables,
 //    each replicated over 16 bank pairs so that lane l only ever reads bank pair l % 16) and a
 //    quarter of a Philox block.
@@ -42,12 +44,20 @@
 #ifndef TMC_GROUP
 #define TMC_GROUP 4        /* events of a Philox block whose table look-ups are issued together (walk loop) */
 #endif
+#ifndef TMC_PPL
+#define TMC_PPL 2          /* photons per lane (independent dependency chains per thread); a cohort is 32 * TMC_PPL photons */
+#endif
+#ifndef TMC_PACKED
+#define TMC_PACKED 7       /* packed fp32 pairs (Blackwell f32x2) in the walk loop, a bit mask: 1 = FFMA2 for the (y, z) update of an
+                              event, 2 = FADD2 for xi of two photons, 4 = FFMA2.RZ for the shell numbers of two photons */
+#endif
 #ifndef TMC_EXPERIMENT
 #define TMC_EXPERIMENT 0   /* timing experiments (tools/experiments.sh); the product is built with 0 */
 #endif
 
 namespace tmc {
 
+constexpr int kPacked = TMC_PACKED;
 constexpr uint32_t kEventsPerBlock = 4u;                    // one 32-bit Philox word per scatter event
 constexpr int kDirEntries = 256;                            // polar midpoints / azimuths (8 bits each)
 // Direction table in shared memory: row k (256 B) = 16 copies of (-ln2 cos, -ln2 sin)(theta_k) followed
@@ -62,7 +72,7 @@ constexpr uint32_t kSmemUserBase = 0x400u;
 constexpr uint32_t kSmemTableAbs = 0x800u;
 constexpr uint32_t kSmemBinsAbs = kSmemTableAbs + kDirTableBytes;
 constexpr int kMaxGenerations = 24;                         // P(survive 24 roulettes) = 1e-24
-constexpr uint32_t kQueueCap = 128u;                        // entries per queued generation and warp
+constexpr uint32_t kQueueCap = 64u * TMC_PPL;               // entries per queued generation and warp: two cohorts
 constexpr uint32_t kQueueFields = 5u;                       // x, y, z, photon offset, fate word
 constexpr uint32_t kQueueBytesPerWarp = 2u * kQueueFields * kQueueCap * 4u;   // generations 1 and 2
 constexpr uint32_t kLanePrivateMaxShells = 512u;
@@ -127,6 +137,36 @@ __device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
     uint64_t r;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
     return r;
+}
+// (c0, c1) += s * (b.x, b.y) as ONE packed instruction (FFMA2 with a scalar first operand): two
+// independent fp32 FMAs, each rounded exactly like fmaf
+__device__ __forceinline__ void fma2_scalar(float s, float2 b, float& c0, float& c1)
+{
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ra) : "f"(s));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(rc));
+}
+// (a0, a1) + (c, c) as one FADD2
+__device__ __forceinline__ void add2_scalar(float a0, float a1, float c, float& r0, float& r1)
+{
+    unsigned long long ra, rc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(rc) : "f"(c));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(ra));
+}
+// the bits of (a0, a1) * s + m rounded toward zero, as one FFMA2.RZ
+__device__ __forceinline__ void fma2_rz_bits(float a0, float a1, float s, float m, uint32_t& r0, uint32_t& r1)
+{
+    unsigned long long ra, rs, rm;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(rs) : "f"(s));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(rm) : "f"(m));
+    asm("fma.rz.f32x2 %0, %0, %1, %2;" : "+l"(ra) : "l"(rs), "l"(rm));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r0), "=r"(r1) : "l"(ra));
 }
 // byte SEL of `word` into byte 1 of the result, byte 0 of `low` into byte 0, zeros above: the byte
 // offset row * 256 + low of a direction-table entry in ONE instruction (PRMT)
@@ -220,7 +260,7 @@ __device__ __noinline__ uint32_t drain_slice(uint32_t* bins, unsigned long long*
 //         NOT the path the north star names (it skips the position update and the direction
 //         resampling), never used for the headline or the roofline figure.
 // PPL:    photons per lane (independent dependency chains per thread); a cohort is 32 * PPL photons.
-template <int ROUNDS, int BLOCK, int MIN_BLOCKS, bool LANE_PRIVATE, bool RADIAL = false, int PPL = 2>
+template <int ROUNDS, int BLOCK, int MIN_BLOCKS, bool LANE_PRIVATE, bool RADIAL = false, int PPL = TMC_PPL>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __grid_constant__ WalkArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];     // [gap | direction table 64 KB | histograms]
@@ -307,6 +347,18 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
         const float r2 = fmaf(z, z, fmaf(y, y, x * x));
         return LANE_PRIVATE ? __saturatef(r2) : r2;
     };
+    // spin + hop (photon.c:35-43 sampled directly, photon.c:22-24): L = log2(xi) <= 0, pol = kappa * (-ln2 cos, -ln2 sin)(theta),
+    // azi = (cos, sin)(phi); the step t = -ln2 * L is folded into the polar entry
+    auto move = [&](float L, float2 pol, float2 azi, float& x, float& y, float& z) {
+        const float ts = L * pol.y;
+        x = fmaf(L, pol.x, x);
+        if constexpr ((kPacked & 1) != 0) {
+            fma2_scalar(ts, azi, y, z);        // one FFMA2
+        } else {
+            y = fmaf(ts, azi.x, y);
+            z = fmaf(ts, azi.y, z);
+        }
+    };
     auto shell_bits = [&](float rad) {
         const uint32_t sb = __float_as_uint(__fmaf_rz(rad, a.shell_scale, 8388608.0f));
         return LANE_PRIVATE ? sb : min(sb, clamp_bits);
@@ -340,10 +392,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             } else {
                 // spin (photon.c:35-43, sampled directly) and move (photon.c:22-24)
                 const float2 azi = lds_f32x2<kSmemTableAbs>(row_offset<0>(v, azimuth_low));
-                const float ts = L * pol.y;
-                px[j] = fmaf(L, pol.x, px[j]);
-                py[j] = fmaf(ts, azi.x, py[j]);
-                pz[j] = fmaf(ts, azi.y, pz[j]);
+                move(L, pol, azi, px[j], py[j], pz[j]);
                 rad = mufu_sqrt(radius_sq(px[j], py[j], pz[j]));
             }
             const uint32_t sb = shell_bits(rad);
@@ -414,41 +463,68 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             take_block(cur);
             constexpr int G = TMC_GROUP;                     // events per group: 1, 2 or 4
             float L[G][PPL];
-            float2 pol[G][PPL], azi[G][PPL];
+            float2 pol[G][PPL];
+            [[maybe_unused]] float2 azi[G][PPL];
             uint32_t off[G][PPL];
+            // photons 2p and 2p+1 of a lane share the packed instructions (TMC_PACKED); an odd last photon goes scalar
             auto look_up = [&](auto first_tag) {
                 constexpr int S0 = decltype(first_tag)::value;
 #pragma unroll
-                for (int e = 0; e < G; ++e)
+                for (int e = 0; e < G; ++e) {
+#pragma unroll
+                    for (int j = 0; j < PPL; j += 2) {
+                        const float f0 = __uint_as_float(__funnelshift_r(r[j][S0 + e], 0x7Fu, 9));      // 1 + m 2^-23
+                        if ((kPacked & 2) && j + 1 < PPL) {             // xi of both photons by one FADD2
+                            float xi0, xi1;
+                            add2_scalar(f0, __uint_as_float(__funnelshift_r(r[j + 1][S0 + e], 0x7Fu, 9)), -kOneMinusHalfUlp, xi0, xi1);
+                            L[e][j] = mufu_lg2(xi0);
+                            L[e][j + 1] = mufu_lg2(xi1);
+                        } else {
+                            L[e][j] = mufu_lg2(f0 - kOneMinusHalfUlp);
+                            if (j + 1 < PPL) L[e][j + 1] = mufu_lg2(__uint_as_float(__funnelshift_r(r[j + 1][S0 + e], 0x7Fu, 9)) - kOneMinusHalfUlp);
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < PPL; ++j) {
                         const uint32_t v = r[j][S0 + e];
-                        L[e][j] = mufu_lg2(__uint_as_float(__funnelshift_r(v, 0x7Fu, 9)) - kOneMinusHalfUlp);
                         pol[e][j] = lds_f32x2<kSmemTableAbs>(row_offset<1>(v, polar_low));
                         if constexpr (!RADIAL) azi[e][j] = lds_f32x2<kSmemTableAbs>(row_offset<0>(v, azimuth_low));
                     }
+                }
             };
             auto walk_group = [&]() {
 #pragma unroll
-                for (int e = 0; e < G; ++e)
+                for (int e = 0; e < G; ++e) {
+                    float rad[PPL];
 #pragma unroll
                     for (int j = 0; j < PPL; ++j) {
-                        float rad;
                         if constexpr (RADIAL) {
                             const float t = L[e][j] * a.radial_step, tmu = L[e][j] * pol[e][j].x;
                             const float r2 = fmaf(px[j] + px[j], tmu, fmaf(t, t, px[j] * px[j]));
                             px[j] = mufu_sqrt(fmaxf(r2, 0.0f));      // the state keeps the true radius,
-                            rad = fminf(px[j], 1.0f);                // the tally sees it clamped to the grid
+                            rad[j] = fminf(px[j], 1.0f);             // the tally sees it clamped to the grid
                         } else {
-                            const float ts = L[e][j] * pol[e][j].y;
-                            px[j] = fmaf(L[e][j], pol[e][j].x, px[j]);
-                            py[j] = fmaf(ts, azi[e][j].x, py[j]);
-                            pz[j] = fmaf(ts, azi[e][j].y, pz[j]);
-                            rad = mufu_sqrt(radius_sq(px[j], py[j], pz[j]));
+                            move(L[e][j], pol[e][j], azi[e][j], px[j], py[j], pz[j]);
+                            rad[j] = mufu_sqrt(radius_sq(px[j], py[j], pz[j]));
                         }
-                        const uint32_t sb = shell_bits(rad);
-                        off[e][j] = LANE_PRIVATE ? shell_offset(sb, lane_low) : (sb << 2) + plain_bias;
                     }
+#pragma unroll
+                    for (int j = 0; j < PPL; j += 2) {
+                        uint32_t sb0, sb1 = 0u;
+                        if ((kPacked & 4) && j + 1 < PPL) {             // the shell numbers of both photons by one FFMA2.RZ
+                            fma2_rz_bits(rad[j], rad[j + 1], a.shell_scale, 8388608.0f, sb0, sb1);
+                            if constexpr (!LANE_PRIVATE) {
+                                sb0 = min(sb0, clamp_bits);
+                                sb1 = min(sb1, clamp_bits);
+                            }
+                        } else {
+                            sb0 = shell_bits(rad[j]);
+                            if (j + 1 < PPL) sb1 = shell_bits(rad[j + 1]);
+                        }
+                        off[e][j] = LANE_PRIVATE ? shell_offset(sb0, lane_low) : (sb0 << 2) + plain_bias;
+                        if (j + 1 < PPL) off[e][j + 1] = LANE_PRIVATE ? shell_offset(sb1, lane_low) : (sb1 << 2) + plain_bias;
+                    }
+                }
             };
             auto tally_group = [&]() {
 #pragma unroll

@@ -1,7 +1,7 @@
 #!/bin/bash
 # tools/experiments.sh — build timing-experiment variants of the library (never shipped):
 #   usage: tools/experiments.sh name1 "flags1" name2 "flags2" ...   ->  tiny_mc_b200/lib/exp/libtinymc_<name>.so
-#   e.g.   tools/experiments.sh ppl1 "-DTMC_PPL=1" oneatomic "-DTMC_EXPERIMENT=1"
+#   e.g.   tools/experiments.sh ppl4 "-DTMC_PPL=4 -DTMC_ONLY_BLOCK=256 -DTMC_DEFAULT_BLOCK_PRIVATE=256 -DTMC_DEFAULT_BLOCK_PLAIN=256"
 set -e
 mkdir -p tiny_mc_b200/lib/exp
 while [ $# -ge 2 ]; do

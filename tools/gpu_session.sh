@@ -95,6 +95,23 @@ batches)   # the batched call (TMC_JSON) against the plain call, C host program,
     TMC_TRACE=1 TMC_JSON=gpurun_out/${prog}.json timeout 300 tiny_mc_b200/bin/$prog 2> gpurun_out/${prog}_json.err | sed -n 8,9p; grep "tmc trace" gpurun_out/${prog}_json.err | tail -1
     TMC_BATCH_STREAMS=1 TMC_TRACE=1 TMC_JSON=gpurun_out/${prog}.json timeout 300 tiny_mc_b200/bin/$prog 2> gpurun_out/${prog}_json1.err | sed -n 8,9p; grep "tmc trace" gpurun_out/${prog}_json1.err | tail -1
   done ;;
+vtests)   # the exact-replay tests against variant libraries: VLIBS="name1 name2" (tiny_mc_b200/lib/exp/libtinymc_<name>.so)
+  for v in ${VLIBS:-}; do
+    TMC_LIB=tiny_mc_b200/lib/exp/libtinymc_$v.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "replay or other_optics or independent_of_split or single_photon" > gpurun_out/pytest_replay_$v.log 2>&1; echo "pytest replay $v rc=$?"; tail -3 gpurun_out/pytest_replay_$v.log
+  done ;;
+vquick)   # quick_bench of every tiny_mc_b200/lib/exp/libtinymc_*.so (PLANS="config:block:per_sm ...")
+  rm -f gpurun_out/quick_variants.jsonl
+  for f in tiny_mc_b200/lib/exp/libtinymc_*.so; do
+    TMC_LIB=$f timeout 300 python tools/quick_bench.py ${PLANS:-default:0:0 highalbedo:0:0:10:22 finegrid:0:0} >> gpurun_out/quick_variants.jsonl 2>> gpurun_out/quick.err; echo "variant $f rc=$?"
+  done
+  python - <<'PY'
+import json
+for l in open("gpurun_out/quick_variants.jsonl"):
+    d = json.loads(l)
+    if "error" in d: print(d); continue
+    print(f"{d['lib'] or 'in-tree':28s} {d['config']:10s} block {d['block']:4d} x grid {d['grid']:3d} flush {d['flush']:4d}  {d['photons_per_s']:.4g} photons/s  {d['events_per_s']:.4g} events/s")
+PY
+  ;;
 mixncu)   # the walk-mix ceiling micro-benchmark alone, with ncu's pipe counters
   timeout 300 ncu --metrics sm__cycles_elapsed.avg,smsp__inst_executed.sum,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,sm__issue_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio,smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio \
       --clock-control none -k regex:k_walk_mix --csv --log-file gpurun_out/mix_ncu.csv tiny_mc_b200/bin/tmc_microbench > gpurun_out/mix_under_ncu.jsonl 2>&1; echo "mixncu rc=$?"; grep -E "k_walk_mix" gpurun_out/mix_ncu.csv | awk -F'","' '{print $(NF-2), $(NF-1), $NF}' | tail -14 ;;
