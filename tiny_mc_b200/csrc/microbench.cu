@@ -276,7 +276,13 @@ __global__ void __launch_bounds__(kBlock) k_atoms_baseline(Out* out, unsigned se
 #define WM_LG2_E_(i) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(e##i));
 #define WM_FMUL_E_(i) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(f##i) : "f"(e##i));
 #define WM_SQRT_(i) asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(f##i));
-// DROP selects what is left out, to see what each instruction class costs inside the mix:
+// the packed forms kernel v9 uses (Blackwell f32x2): the (y, z) update of one chain as one FFMA2 with a scalar first
+// operand, xi and the shell number of two chains as one FADD2 / FFMA2.RZ
+#define WM_FFMA2_YZ_(i) asm volatile("{ .reg .b64 a, b, c; mov.b64 a, {%2, %2}; mov.b64 b, {%3, %4}; mov.b64 c, {%0, %1}; fma.rn.f32x2 c, a, b, c; mov.b64 {%0, %1}, c; }" : "+f"(y##i), "+f"(z##i) : "f"(f##i), "f"(p##i), "f"(q##i));
+#define WM_FADD2_E_(i, j) asm volatile("{ .reg .b64 a, c; mov.b64 a, {%0, %1}; mov.b64 c, {%2, %2}; add.rn.f32x2 a, a, c; mov.b64 {%0, %1}, a; }" : "+f"(e##i), "+f"(e##j) : "f"(-0.99999994f));
+#define WM_FFMA2_RZ_(i, j) asm volatile("{ .reg .b64 a, b, c; mov.b64 a, {%0, %1}; mov.b64 b, {%2, %2}; mov.b64 c, {%3, %3}; fma.rz.f32x2 a, a, b, c; mov.b64 {%0, %1}, a; }" : "+f"(f##i), "+f"(f##j) : "f"(ca), "f"(cb));
+#define PAIRS4(X) X(0, 1) X(2, 3) X(4, 5) X(6, 7)
+// DROP selects what is left out, to see what each instruction class costs inside the mix (6 = nothing left out, packed forms):
 // 0 nothing, 1 the three PRMT and the SHF (ALU pipe), 2 the Philox quarter block, 3 the shared-memory instructions,
 // 4 the two MUFU, 5 the FP32 arithmetic
 template <int DROP>
@@ -294,12 +300,21 @@ __global__ void __launch_bounds__(512, 1) k_walk_mix(Out* out, unsigned seed)
     float g0 = ca, g1 = ca, g2 = ca, g3 = ca, g4 = ca, g5 = ca, g6 = ca, g7 = ca, h0 = cb, h1 = cb, h2 = cb, h3 = cb, h4 = cb, h5 = cb, h6 = cb, h7 = cb;
     float p0 = ca, p1 = ca, p2 = ca, p3 = ca, p4 = ca, p5 = ca, p6 = ca, p7 = ca, q0 = cb, q1 = cb, q2 = cb, q3 = cb, q4 = cb, q5 = cb, q6 = cb, q7 = cb;
     float e0 = 1.5f, e1 = 1.5f, e2 = 1.5f, e3 = 1.5f, e4 = 1.5f, e5 = 1.5f, e6 = 1.5f, e7 = 1.5f;
+    float y0 = cb, y1 = cb, y2 = cb, y3 = cb, y4 = cb, y5 = cb, y6 = cb, y7 = cb, z0 = ca, z1 = ca, z2 = ca, z3 = ca, z4 = ca, z5 = ca, z6 = ca, z7 = ca;
     __syncthreads();
     const long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < kIters / 4; ++it) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {      // 8 events each; 4 wide steps in the first half, 5 in the second
+            if (DROP == 6) {                        // kernel v9's mix: 26.5 instructions per event
+                REP8(WM_SHFF_) PAIRS4(WM_FADD2_E_) REP8(WM_LG2_E_) REP8(WM_PRMT_A_) REP8(WM_PRMT_B_) REP8(WM_LDS_A_) REP8(WM_LDS_B_)
+                REP8(WM_FMUL_E_) REP8(WM_FFMA_G_) REP8(WM_FFMA2_YZ_) REP8(FMUL_) REP8(FFMA_) REP8(FFMA_) REP8(WM_SQRT_) PAIRS4(WM_FFMA2_RZ_)
+                REP8(WM_PRMT_C_) REP8(WM_RED_) REP8(WM_RED2_)
+                REP8(WIDE_STEP_) REP8(WIDE_STEP_) REP8(WIDE_STEP_) REP8(WIDE_STEP_)
+                if (half == 0) { REP8(EXTRA_LOP_) } else { REP8(WIDE_STEP_) }
+                continue;
+            }
             if (DROP != 1) { REP8(WM_SHFF_) }
             if (DROP != 5) { REP8(WM_FADD_E_) }
             if (DROP != 4) { REP8(WM_LG2_E_) }
@@ -319,7 +334,7 @@ __global__ void __launch_bounds__(512, 1) k_walk_mix(Out* out, unsigned seed)
     const long long t1 = clock64();
     __syncthreads();
     if (threadIdx.x == 0) out[blockIdx.x].cycles = t1 - t0;
-    if ((F_SINK ^ U_SINK ^ a0 ^ b0 ^ c0 ^ __float_as_uint(e0 + g0 + h0 + p0 + q0)) == 0x12345u) out[blockIdx.x].sink = 1;
+    if ((F_SINK ^ U_SINK ^ a0 ^ b0 ^ c0 ^ __float_as_uint(e0 + g0 + h0 + p0 + q0 + y0 + y1 + y2 + y3 + y4 + y5 + y6 + y7 + z0 + z1 + z2 + z3 + z4 + z5 + z6 + z7)) == 0x12345u) out[blockIdx.x].sink = 1;
 }
 
 // The same mix at twice the occupancy: four chains per thread (so that 64 registers suffice), two 512-thread blocks
@@ -464,6 +479,7 @@ int main(int argc, char** argv)
         mix("k_walk_mix_no_shared", k_walk_mix<3>, 456.0 - 64.0);
         mix("k_walk_mix_no_mufu", k_walk_mix<4>, 456.0 - 32.0);
         mix("k_walk_mix_no_fp32", k_walk_mix<5>, 456.0 - 144.0);
+        mix("k_walk_mix_packed", k_walk_mix<6>, 456.0 - 32.0);
         {   // 32 warps per SM: two blocks per SM, four chains per thread (one extra LOP3 per event for the 7-bit shell mask)
             const size_t b2 = 0x800 + 0x10000 + 0x8000;
             CK(cudaFuncSetAttribute(k_walk_mix_32warps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2));

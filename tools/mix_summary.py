@@ -10,7 +10,7 @@ for r in rows[1:]:
     d = dict(zip(hdr, r))
     data.setdefault(d["Kernel Name"].split("(")[0], {})[d["Metric Name"]] = float(d["Metric Value"].replace(",", ""))
 names = {"k_walk_mix<0>": "the walk's mix", "k_walk_mix<1>": "without the 3 PRMT + SHF", "k_walk_mix<2>": "without the Philox quarter block",
-         "k_walk_mix<3>": "without LDS / RED", "k_walk_mix<4>": "without the 2 MUFU", "k_walk_mix<5>": "without the FP32 arithmetic",
+         "k_walk_mix<3>": "without LDS / RED", "k_walk_mix<4>": "without the 2 MUFU", "k_walk_mix<5>": "without the FP32 arithmetic", "k_walk_mix<6>": "kernel v9's mix: packed f32x2 forms (FFMA2 for (y, z), FADD2 / FFMA2.RZ per two chains)",
          "k_walk_mix_32warps": "the walk's mix at 32 warps per SM (4 chains per thread, +0.5 LOP3 per event)"}
 print("| kernel | what | instr / event | cycles / event / SMSP | issue slots used % | FMA-heavy % | ALU % | XU % | shared wavefronts / clk / SM |")
 print("|---|---|---:|---:|---:|---:|---:|---:|---:|")

@@ -38,7 +38,7 @@ for k, (addr, op, w1) in enumerate(ins):
 best = None
 for s, e in loops:
     n_mufu = sum("MUFU" in ins[k][1] for k in range(s, e + 1))
-    if n_mufu >= 16 and (best is None or e - s < best[1] - best[0]):
+    if n_mufu >= 32 and (best is None or e - s < best[1] - best[0]):
         best = (s, e, n_mufu)
 s, e, n_mufu = best
 tot = 0

@@ -1,7 +1,7 @@
 #!/bin/bash
 # tools/sass_stats.sh <lib.so> <kernel-substring> — SASS opcode histogram of one kernel (whole body) and of its hottest loop.
 lib=$1; pat=$2
-cuobjdump -sass "$lib" | awk -v pat="$pat" '/Function :/{f=index($0,pat)>0} f' | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -e 's#/\*[0-9a-f]*\*/##g' | awk '{$1=$1};1' > /tmp/sass_kernel.txt
+cuobjdump -sass "$lib" | awk -v pat="$pat" '/Function :/{f=index($0,pat)>0} f' | grep -E "^\s+/\*[0-9a-f]{4,5}\*/" | sed -e 's#/\*[0-9a-f]*\*/##g' | awk '{$1=$1};1' > /tmp/sass_kernel.txt
 echo "total instructions: $(wc -l < /tmp/sass_kernel.txt)"
 python3 - <<'PY'
 import re,collections
@@ -11,7 +11,8 @@ addr=0
 ins=[]
 for l in lines:
     ins.append(l)
-# addresses are implicit: 16 bytes per instruction
+# addresses are implicit: 16 bytes per instruction.  The hot loop = the smallest loop holding two full Philox
+# blocks of two photons per lane (16 events = 32 MUFU): the full-cohort instantiation of the walk loop
 loops=[]
 for i,l in enumerate(ins):
     m=re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?0x([0-9a-f]+)",l)
@@ -21,7 +22,7 @@ for i,l in enumerate(ins):
 best=None
 for (s,e) in loops:
     body=ins[s:e+1]
-    if any("MUFU" in b for b in body):
+    if sum("MUFU" in b for b in body) >= 32:
         if best is None or (e-s)<(best[1]-best[0]): best=(s,e)
 if best:
     s,e=best
