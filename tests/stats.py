@@ -31,3 +31,11 @@ def literal_sigma_z(heat_a, heat2_a, n_a, heat_b, heat2_b, n_b):
         vb = (heat2_b - heat_b**2 / n_b) / n_b**2
         z = (heat_a / n_a - heat_b / n_b) / np.sqrt(va + vb)
     return z
+
+
+def fnv64(words) -> str:
+    """FNV-1a (64 bit) over the little-endian bytes of u64 tally words (the same hash as bench.py's checks.tally_hash)."""
+    h = 0xCBF29CE484222325
+    for b in np.asarray(words).astype("<u8").tobytes():
+        h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"

@@ -19,7 +19,7 @@ import subprocess
 import numpy as np
 import pytest
 from conftest import GOLDEN, ROOT
-from stats import batch_means_z, literal_sigma_z
+from stats import batch_means_z, fnv64, literal_sigma_z
 
 pytestmark = pytest.mark.gpu
 
@@ -43,6 +43,18 @@ def test_gpu_equals_cpu_replay_of_the_same_stream(gpu, orc, name, n, flip_tol):
     moved = np.abs(heat_fx.astype(np.int64) - r_heat.astype(np.int64)).sum() / 2
     assert moved <= flip_tol * r_heat.sum(), f"{moved / r_heat.sum():.2e} of the weight changed shell (MUFU vs libm)"
     assert info.retries == 0
+
+
+def test_tallies_are_the_committed_words(gpu):
+    """The exact tally words of fixed photon ranges, hashed (tests/golden/make_tally_hashes.py): an optimisation of
+    the kernel that keeps its arithmetic (scheduling, packed f32x2 forms, launch shapes, queue layout ...) must
+    reproduce them bit for bit; the default-optics entry is bench.py's checks.tally_hash."""
+    import json
+    golden = json.loads((GOLDEN / "tally_hashes.json").read_text())
+    for name, g in golden.items():
+        h, h2 = gpu.photons_fx(name.split("_")[0], g["seed"], g["first"], g["photons"])
+        assert gpu.last_run_info().events == g["events"], name
+        assert fnv64(np.concatenate([h, h2])) == g["fnv1a64"], name
 
 
 @pytest.mark.parametrize("rounds", [7, 10])
