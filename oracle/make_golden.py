@@ -22,6 +22,8 @@ only — the fixtures are what travels to the GPU box and into git).
                            from the xoshiro port and from the unmodified reference on PCG32.
   *_batches_default_1e9.npz  default optics at 64 x 2^24 = 1.07e9 photons per reference (unmodified reference on
                            PCG32, port on xoshiro256**): per-shell precision 0.01 %.  Opt-in: `make_golden.py default_1e9`.
+  *_batches_highalbedo_1e7.npz  config 4's optics at 64 x 2^18 = 1.68e7 photons per reference (7168 events per photon:
+                           1.2e11 events each).  Opt-in: `make_golden.py highalbedo_1e7` (30 minutes on 8 cores).
   *_pershell_finegrid_1e9.npz  config 5 per 5 um shell at 256 x 2^22 = 1.07e9 photons per reference.  Opt-in:
                            `make_golden.py finegrid_pershell_1e9` (20 minutes on 8 cores).
   headless_asshipped.txt   stdout of the reference `headless` built exactly as its Makefile does,
@@ -115,6 +117,14 @@ def main():
             np.savez_compressed(GOLD / f"{tag}_batches_default_1e9.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
                                 photons_per_batch=n, chunk=256)
             print(f"default 1e9 ({tag}): total/photon {heat.sum() / (nb * n):.7f}, wall {wall:.1f} s")
+    if "highalbedo_1e7" in only:   # opt-in (30 minutes on 8 cores): config 4's optics at 64 x 2^18 = 1.68e7 photons per reference
+        nb, n = 64, 1 << 18
+        seeds = [110000 + 19 * b for b in range(nb)]
+        for tag, kw in (("ref_pcg", dict(impl="reference_pcg")), ("port_xoshiro", dict(impl="port", rng="xoshiro"))):
+            heat, heat2, _, secs, wall = orc.run_batches("highalbedo", seeds, n, chunk=8, **kw)
+            np.savez_compressed(GOLD / f"{tag}_batches_highalbedo_1e7.npz", heat=heat, heat2=heat2, seeds=np.array(seeds),
+                                photons_per_batch=n, chunk=8)
+            print(f"highalbedo 1e7 ({tag}): total/photon {heat.sum() / (nb * n):.7f}, wall {wall:.1f} s", flush=True)
     if "finegrid_pershell_1e9" in only:      # opt-in (20 minutes on 8 cores): config 5 per 5 um shell at 1.07e9 photons per reference
         nb, n = 256, 1 << 22
         seeds = [90000 + 17 * b for b in range(nb)]

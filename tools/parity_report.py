@@ -61,6 +61,22 @@ for fixture in ("ref_pcg", "port_xoshiro"):
                                             absorbed_per_photon_gpu=float(heat9.sum() / (nb * n)),
                                             absorbed_per_photon_reference=float(ref["heat"].sum() / (ref["heat"].shape[0] * n_ref)),
                                             z=[round(float(v), 2) for v in z])
+# config 4's optics against the 1.68e7-photon references (6.7e7 GPU photons = 4.8e11 events)
+if (GOLD / "ref_pcg_batches_highalbedo_1e7.npz").exists():
+    nb, n = 64, 1 << 20
+    bh, bh2 = tmc.photons_fx_batches("highalbedo", 0xA1BED0, 0, nb * n, nb)
+    heat7 = np.stack([tmc.capi.fx_to_float64("highalbedo", bh[b], bh2[b])[0] for b in range(nb)])
+    for fixture in ("ref_pcg", "port_xoshiro"):
+        ref = np.load(GOLD / f"{fixture}_batches_highalbedo_1e7.npz")
+        n_ref = int(ref["photons_per_batch"])
+        z, ok = batch_means_z(heat7, n, ref["heat"], n_ref)
+        rel = np.sqrt((heat7 / n).var(axis=0, ddof=1) / nb + (ref["heat"] / n_ref).var(axis=0, ddof=1) / ref["heat"].shape[0]) / (heat7 / n).mean(axis=0)
+        out[f"highalbedo_1e7_vs_{fixture}"] = dict(gpu_photons=nb * n, reference_photons=ref["heat"].shape[0] * n_ref, shells_tested=int(ok.sum()),
+                                                   max_abs_z=float(np.abs(z).max()), rms_z=float(np.sqrt((z ** 2).mean())), mean_z=float(z.mean()),
+                                                   shells_beyond_3_sigma=int((np.abs(z) > 3).sum()), median_relative_sigma_per_shell=float(np.median(rel)),
+                                                   absorbed_per_photon_gpu=float(heat7.sum() / (nb * n)),
+                                                   absorbed_per_photon_reference=float(ref["heat"].sum() / (ref["heat"].shape[0] * n_ref)),
+                                                   z=[round(float(v), 2) for v in z])
 for name, nb, n in (("default", 64, 1 << 22), ("highalbedo", 64, 1 << 15), ("finegrid", 64, 1 << 22)):
     ref = np.load(GOLD / f"port_xoshiro_batches_{name}.npz")
     n_ref = int(ref["photons_per_batch"])
