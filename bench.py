@@ -175,8 +175,8 @@ def emit(line: dict):
 # ------------------------------------------------------------------------------ our arm
 NAMED = {   # photons per step on one GPU (N = 1), photons per GPU per step on N > 1 GPUs (weak scaling)
     "default": ((1 << 26, "BASELINE configs[1]"), 1 << 29),          # 8 x 2^29 = 2^32 = configs[2]
-    # 2^22 photons = 3e10 events per step on one GPU: ~28 cohorts per warp, so the one-cohort tail is ~1 %
-    "highalbedo": ((1 << 22, "BASELINE configs[3] optics, 2^22-photon steps"), 1 << 23),
+    # 2^24 photons = 1.2e11 events per step on one GPU: ~110 cohorts per warp, so the one-cohort tail is ~1 % (2^22: 4 %)
+    "highalbedo": ((1 << 24, "BASELINE configs[3] optics, 2^24-photon steps"), 1 << 27),     # 8 x 2^27 = 2^30 = configs[3]
     "finegrid": ((1 << 26, "BASELINE configs[4] optics, 2^26-photon steps"), 1 << 27),       # 8 x 2^27 = 2^30 = configs[4]
 }
 CONFIGS2_PHOTONS = 1 << 32                      # BASELINE configs[2]: 2^32 photons sharded over 2 / 4 / 8 GPUs

@@ -17,7 +17,7 @@
 //    roulette with its photon's fate word; the ~10 % survivors are parked in a per-warp queue
 //    of the next generation (global scratch, a few accesses per cohort), the warp immediately
 //    regenerates 64 fresh photons in place (or, when 64 survivors have accumulated, a full
-//    cohort of them).  Generations beyond the second (1e-3 of the photons) continue in place
+//    cohort of them).  Generations beyond the third (1e-4 of the photons) continue in place
 //    with the dead lanes masked.
 //  * Random stream "tmc-stream-4": Philox4x32-R keyed by the seed, counter = (photon index,
 //    block).  One Philox block = FOUR events, one 32-bit word each; event e of a photon is word
@@ -74,7 +74,11 @@ constexpr uint32_t kSmemBinsAbs = kSmemTableAbs + kDirTableBytes;
 constexpr int kMaxGenerations = 24;                         // P(survive 24 roulettes) = 1e-24
 constexpr uint32_t kQueueCap = 64u * TMC_PPL;               // entries per queued generation and warp: two cohorts
 constexpr uint32_t kQueueFields = 5u;                       // x, y, z, photon offset, fate word
-constexpr uint32_t kQueueBytesPerWarp = 2u * kQueueFields * kQueueCap * 4u;   // generations 1 and 2
+#ifndef TMC_QUEUED_GENS
+#define TMC_QUEUED_GENS 3  /* generations whose survivors are parked until a full cohort has accumulated (1 .. TMC_QUEUED_GENS) */
+#endif
+constexpr uint32_t kQueuedGens = TMC_QUEUED_GENS;
+constexpr uint32_t kQueueBytesPerWarp = kQueuedGens * kQueueFields * kQueueCap * 4u;
 constexpr uint32_t kLanePrivateMaxShells = 512u;
 
 struct GenPlan {
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     uint32_t* const bins = table + kDirTableBytes / 4u;
     const uint32_t plain_bins = a.shells + 31u;                              // per kind, plain layout
     const uint32_t nwords = LANE_PRIVATE ? a.shells * 64u : 2u * plain_bins;
-    // this warp's survivor queues: [generation 1|2]{uint4 (x, y, z, photon offset)[kQueueCap], fate[kQueueCap]}, in global memory (a few
+    // this warp's survivor queues: [generation 1|2|3]{uint4 (x, y, z, photon offset)[kQueueCap], fate[kQueueCap]}, in global memory (a few
     // accesses per cohort; L2-resident), so that shared memory holds only the table and tallies
     uint32_t* const queue = a.queues + static_cast<size_t>(blockIdx.x * WARPS + wid) * (kQueueBytesPerWarp / 4u);
 
@@ -364,6 +368,56 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
         return LANE_PRIVATE ? sb : min(sb, clamp_bits);
     };
 
+    // The lane's PPL photons share packed instructions in pairs (2p, 2p+1); an odd last photon goes scalar.
+    // hop (photon.c:21): L = log2(xi) <= 0 for the event word of every photon; the step t = -ln2 * L is folded into the polar table
+    auto log2_xi = [&](const uint32_t (&w)[PPL], float (&L)[PPL]) {
+#pragma unroll
+        for (int j = 0; j < PPL; j += 2) {
+            const float f0 = __uint_as_float(__funnelshift_r(w[j], 0x7Fu, 9));          // 0x3F800000 | m: 1 + m 2^-23
+            if ((kPacked & 2) && j + 1 < PPL) {                                         // xi of both photons by one FADD2
+                float xi0, xi1;
+                add2_scalar(f0, __uint_as_float(__funnelshift_r(w[j + 1], 0x7Fu, 9)), -kOneMinusHalfUlp, xi0, xi1);
+                L[j] = mufu_lg2(xi0);
+                L[j + 1] = mufu_lg2(xi1);
+            } else {
+                L[j] = mufu_lg2(f0 - kOneMinusHalfUlp);
+                if (j + 1 < PPL) L[j + 1] = mufu_lg2(__uint_as_float(__funnelshift_r(w[j + 1], 0x7Fu, 9)) - kOneMinusHalfUlp);
+            }
+        }
+    };
+    // drop (photon.c:26-29): byte offset of the lane's heat word for every photon's (clamped) radius
+    auto tally_offsets = [&](const float (&rad)[PPL], uint32_t (&off)[PPL]) {
+#pragma unroll
+        for (int j = 0; j < PPL; j += 2) {
+            uint32_t sb0, sb1 = 0u;
+            if ((kPacked & 4) && j + 1 < PPL) {                                         // both shell numbers by one FFMA2.RZ
+                fma2_rz_bits(rad[j], rad[j + 1], a.shell_scale, 8388608.0f, sb0, sb1);
+                if constexpr (!LANE_PRIVATE) {
+                    sb0 = min(sb0, clamp_bits);
+                    sb1 = min(sb1, clamp_bits);
+                }
+            } else {
+                sb0 = shell_bits(rad[j]);
+                if (j + 1 < PPL) sb1 = shell_bits(rad[j + 1]);
+            }
+            off[j] = LANE_PRIVATE ? shell_offset(sb0, lane_low) : (sb0 << 2) + plain_bias;
+            if (j + 1 < PPL) off[j + 1] = LANE_PRIVATE ? shell_offset(sb1, lane_low) : (sb1 << 2) + plain_bias;
+        }
+    };
+    // spin + hop of one photon for one event; returns the radius the tally sees
+    auto walk_one = [&](float L, float2 pol, float2 azi, int j) {
+        if constexpr (RADIAL) {
+            // px holds the radius: r'^2 = r^2 + t^2 + 2 r (t mu), >= 0 up to rounding
+            const float t = L * a.radial_step, tmu = L * pol.x;
+            const float r2 = fmaf(px[j] + px[j], tmu, fmaf(t, t, px[j] * px[j]));
+            px[j] = mufu_sqrt(fmaxf(r2, 0.0f));      // the state keeps the true radius,
+            return fminf(px[j], 1.0f);               // the tally sees it clamped to the grid (photon.c:27-29)
+        } else {
+            move(L, pol, azi, px[j], py[j], pz[j]);
+            return mufu_sqrt(radius_sq(px[j], py[j], pz[j]));
+        }
+    };
+
     // One scatter event (reference photon.c:21-43) from word S of the current Philox block for
     // every photon of the lane: spin, hop, drop.  `dep` / `dep2` are the warp-uniform deposit
     // (1-albedo) * w and its rescaled square.  Bits of the event word v:
@@ -375,45 +429,30 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     auto event = [&](auto slot_tag, auto partial_tag, uint32_t dep, uint32_t dep2) {
         constexpr int S = decltype(slot_tag)::value;
         constexpr bool PARTIAL = decltype(partial_tag)::value;
+        uint32_t w[PPL], off[PPL];
+        float L[PPL], rad[PPL];
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) w[j] = r[j][S];
+        log2_xi(w, L);
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
-            const uint32_t v = r[j][S];
-            // hop: L = log2(xi) <= 0, step t = -ln2 * L (photon.c:21); -ln2 is folded into the polar table
-            const float f = __uint_as_float(__funnelshift_r(v, 0x7Fu, 9));       // 0x3F800000 | m: 1 + m 2^-23
-            const float L = mufu_lg2(f - kOneMinusHalfUlp);
-            const float2 pol = lds_f32x2<kSmemTableAbs>(row_offset<1>(v, polar_low));
-            float rad;
-            if constexpr (RADIAL) {
-                // px holds the radius: r'^2 = r^2 + t^2 + 2 r (t mu), >= 0 up to rounding
-                const float t = L * a.radial_step, tmu = L * pol.x;
-                const float r2 = fmaf(px[j] + px[j], tmu, fmaf(t, t, px[j] * px[j]));
-                px[j] = mufu_sqrt(fmaxf(r2, 0.0f));      // the state keeps the true radius,
-                rad = fminf(px[j], 1.0f);                // the tally sees it clamped to the grid (photon.c:27-29)
-            } else {
-                // spin (photon.c:35-43, sampled directly) and move (photon.c:22-24)
-                const float2 azi = lds_f32x2<kSmemTableAbs>(row_offset<0>(v, azimuth_low));
-                move(L, pol, azi, px[j], py[j], pz[j]);
-                rad = mufu_sqrt(radius_sq(px[j], py[j], pz[j]));
-            }
-            const uint32_t sb = shell_bits(rad);
-            if constexpr (LANE_PRIVATE) {
-                const uint32_t off = shell_offset(sb, lane_low);
-                if (!PARTIAL || act[j]) {
-#if TMC_EXPERIMENT == 1   /* one atomic instead of two (wrong tallies; timing experiment only) */
-                    red_shared_add<kSmemBinsAbs>(off, dep + dep2);
-#else
-                    red_shared_add<kSmemBinsAbs>(off, dep);
-                    red_shared_add<kSmemBinsAbs + 128u>(off, dep2);
-#endif
-                }
-            } else {
-                const uint32_t off = (sb << 2) + plain_bias;
-                if (!PARTIAL || act[j]) {
-                    red_shared_add<kSmemBinsAbs>(off, dep);
-                    red_shared_add<kSmemBinsAbs>(off + heat2_off, dep2);
-                }
-            }
+            const float2 pol = lds_f32x2<kSmemTableAbs>(row_offset<1>(w[j], polar_low));
+            float2 azi = pol;
+            if constexpr (!RADIAL) azi = lds_f32x2<kSmemTableAbs>(row_offset<0>(w[j], azimuth_low));
+            rad[j] = walk_one(L[j], pol, azi, j);
         }
+        tally_offsets(rad, off);
+#pragma unroll
+        for (int j = 0; j < PPL; ++j)
+            if (!PARTIAL || act[j]) {
+#if TMC_EXPERIMENT == 1   /* one atomic instead of two (wrong tallies; timing experiment only) */
+                red_shared_add<kSmemBinsAbs>(off[j], dep + dep2);
+#else
+                red_shared_add<kSmemBinsAbs>(off[j], dep);
+                if constexpr (LANE_PRIVATE) red_shared_add<kSmemBinsAbs + 128u>(off[j], dep2);
+                else red_shared_add<kSmemBinsAbs>(off[j] + heat2_off, dep2);
+#endif
+            }
     };
 
     // Walk generation g for the photons held by the warp, then play roulette (photon.c:45-49).
@@ -466,29 +505,18 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             float2 pol[G][PPL];
             [[maybe_unused]] float2 azi[G][PPL];
             uint32_t off[G][PPL];
-            // photons 2p and 2p+1 of a lane share the packed instructions (TMC_PACKED); an odd last photon goes scalar
             auto look_up = [&](auto first_tag) {
                 constexpr int S0 = decltype(first_tag)::value;
 #pragma unroll
                 for (int e = 0; e < G; ++e) {
+                    uint32_t w[PPL];
 #pragma unroll
-                    for (int j = 0; j < PPL; j += 2) {
-                        const float f0 = __uint_as_float(__funnelshift_r(r[j][S0 + e], 0x7Fu, 9));      // 1 + m 2^-23
-                        if ((kPacked & 2) && j + 1 < PPL) {             // xi of both photons by one FADD2
-                            float xi0, xi1;
-                            add2_scalar(f0, __uint_as_float(__funnelshift_r(r[j + 1][S0 + e], 0x7Fu, 9)), -kOneMinusHalfUlp, xi0, xi1);
-                            L[e][j] = mufu_lg2(xi0);
-                            L[e][j + 1] = mufu_lg2(xi1);
-                        } else {
-                            L[e][j] = mufu_lg2(f0 - kOneMinusHalfUlp);
-                            if (j + 1 < PPL) L[e][j + 1] = mufu_lg2(__uint_as_float(__funnelshift_r(r[j + 1][S0 + e], 0x7Fu, 9)) - kOneMinusHalfUlp);
-                        }
-                    }
+                    for (int j = 0; j < PPL; ++j) w[j] = r[j][S0 + e];
+                    log2_xi(w, L[e]);
 #pragma unroll
                     for (int j = 0; j < PPL; ++j) {
-                        const uint32_t v = r[j][S0 + e];
-                        pol[e][j] = lds_f32x2<kSmemTableAbs>(row_offset<1>(v, polar_low));
-                        if constexpr (!RADIAL) azi[e][j] = lds_f32x2<kSmemTableAbs>(row_offset<0>(v, azimuth_low));
+                        pol[e][j] = lds_f32x2<kSmemTableAbs>(row_offset<1>(w[j], polar_low));
+                        if constexpr (!RADIAL) azi[e][j] = lds_f32x2<kSmemTableAbs>(row_offset<0>(w[j], azimuth_low));
                     }
                 }
             };
@@ -497,33 +525,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                 for (int e = 0; e < G; ++e) {
                     float rad[PPL];
 #pragma unroll
-                    for (int j = 0; j < PPL; ++j) {
-                        if constexpr (RADIAL) {
-                            const float t = L[e][j] * a.radial_step, tmu = L[e][j] * pol[e][j].x;
-                            const float r2 = fmaf(px[j] + px[j], tmu, fmaf(t, t, px[j] * px[j]));
-                            px[j] = mufu_sqrt(fmaxf(r2, 0.0f));      // the state keeps the true radius,
-                            rad[j] = fminf(px[j], 1.0f);             // the tally sees it clamped to the grid
-                        } else {
-                            move(L[e][j], pol[e][j], azi[e][j], px[j], py[j], pz[j]);
-                            rad[j] = mufu_sqrt(radius_sq(px[j], py[j], pz[j]));
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < PPL; j += 2) {
-                        uint32_t sb0, sb1 = 0u;
-                        if ((kPacked & 4) && j + 1 < PPL) {             // the shell numbers of both photons by one FFMA2.RZ
-                            fma2_rz_bits(rad[j], rad[j + 1], a.shell_scale, 8388608.0f, sb0, sb1);
-                            if constexpr (!LANE_PRIVATE) {
-                                sb0 = min(sb0, clamp_bits);
-                                sb1 = min(sb1, clamp_bits);
-                            }
-                        } else {
-                            sb0 = shell_bits(rad[j]);
-                            if (j + 1 < PPL) sb1 = shell_bits(rad[j + 1]);
-                        }
-                        off[e][j] = LANE_PRIVATE ? shell_offset(sb0, lane_low) : (sb0 << 2) + plain_bias;
-                        if (j + 1 < PPL) off[e][j + 1] = LANE_PRIVATE ? shell_offset(sb1, lane_low) : (sb1 << 2) + plain_bias;
-                    }
+                    for (int j = 0; j < PPL; ++j) rad[j] = walk_one(L[e][j], pol[e][j], RADIAL ? pol[e][j] : azi[e][j], j);
+                    tally_offsets(rad, off[e]);
                 }
             };
             auto tally_group = [&]() {
@@ -656,15 +659,20 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     const uint32_t count = static_cast<uint32_t>(a.count);
     const uint32_t n_cohorts = (count + COHORT - 1u) / COHORT;
     uint32_t cohort = blockIdx.x * WARPS + wid;
-    uint32_t nq[2] = { 0u, 0u };            // fill of this warp's generation-1 and -2 queues
+    uint32_t nq[kQueuedGens] = {};          // fill of this warp's survivor queues (generations 1 .. kQueuedGens)
 
     for (;;) {
+        // a full cohort of parked survivors (deepest generation first), else fresh photons, else the leftovers
+        // (shallowest first: their survivors feed the deeper queues)
+        static_assert(kQueuedGens == 2u || kQueuedGens == 3u, "TMC_QUEUED_GENS must be 2 or 3");
         uint32_t g, take;
-        if (nq[1] >= COHORT) { g = 2u; take = COHORT; }
+        if (kQueuedGens >= 3u && nq[kQueuedGens - 1u] >= COHORT) { g = 3u; take = COHORT; }
+        else if (nq[1] >= COHORT) { g = 2u; take = COHORT; }
         else if (nq[0] >= COHORT) { g = 1u; take = COHORT; }
         else if (cohort < n_cohorts) { g = 0u; take = min(COHORT, count - cohort * COHORT); }
         else if (nq[0] > 0u) { g = 1u; take = nq[0]; }
         else if (nq[1] > 0u) { g = 2u; take = nq[1]; }
+        else if (kQueuedGens >= 3u && nq[kQueuedGens - 1u] > 0u) { g = 3u; take = nq[kQueuedGens - 1u]; }
         else break;
 
         if (g == 0u) {                      // regenerate: a cohort of fresh photons at the origin
@@ -702,7 +710,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             if (partial) phase(BoolTag<true>{}, g);
             else phase(BoolTag<false>{}, g);
             if (g + 1u >= a.n_gen) break;
-            if (g + 1u <= 2u) {             // park the survivors for a later full cohort
+            if (g + 1u <= kQueuedGens) {    // park the survivors for a later full cohort
                 uint32_t* q = queue + g * (kQueueFields * kQueueCap);
 #pragma unroll
                 for (int j = 0; j < PPL; ++j) {
@@ -717,7 +725,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
                 __syncwarp();
                 break;
             }
-            // deeper generations (1e-3 of the photons): the survivors continue in place
+            // deeper generations (1e-4 of the photons): the survivors continue in place
             bool any = false;
 #pragma unroll
             for (int j = 0; j < PPL; ++j) {
