@@ -88,7 +88,8 @@ int tmc_abi_version(void);
 /* Tunables: "philox_rounds" (10 = default, or 7), "block_threads" (128..1024), "blocks_per_sm"
  * (1..4: residency, and with it the register budget of the kernel variant),
  * "flush_iters", "nccl_reduce" (1 = NCCL, 0 = host-side sum; default 1), "tally_layout"
- * (0 = auto, 1 = one histogram per block, 2 = one per lane), "tally_check_bits" (31; tests lower
+ * (0 = auto, 1 = one histogram per block with per-lane slots for the overflow shell, 2 = one histogram per lane,
+ * 3 = one per block with a single overflow word: auto picks it for grids no photon leaves), "tally_check_bits" (31; tests lower
  * it to exercise the TMC_ERR_TALLY_RANGE retry), "walk_mode" (0 = the 3-D walk of reference
  * photon.c:20-50; 1 = a reduced radial walk, r'^2 = r^2 + t^2 + 2 r t mu, distribution-identical for
  * this isotropic problem: a cross-check, never the benchmarked path; default block shape only),

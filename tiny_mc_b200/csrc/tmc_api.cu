@@ -64,7 +64,8 @@ struct Options {
     int blocks_per_sm = 0;   // 0 = occupancy
     int flush_iters = 0;     // 0 = auto
     int nccl_reduce = 1;
-    int tally_layout = 0;    // 0 = auto, 1 = plain per-block histogram, 2 = lane-private
+    int tally_layout = 0;    // 0 = auto, 1 = plain per-block histogram (per-lane overflow slots), 2 = lane-private,
+                             // 3 = plain with the saturating clamp (one word for the overflow shell)
     int tally_check_bits = 31;   // a drained u32 word >= 2^bits triggers the retry (tests lower it)
     int walk_mode = 0;           // 0 = the 3-D walk (the product), 1 = the reduced radial walk (cross-check only)
     int batch_streams = 2;       // streams per device the launches of a batched call alternate between (1 or 2)
@@ -254,8 +255,20 @@ KernelFn radial_kernel(int block, int per_sm, bool lane_private)
     return nullptr;
 }
 
-KernelFn pick_kernel(int rounds, int block, int per_sm, bool lane_private, bool radial)
+// the one-histogram layout with the saturating clamp (walk_kernel.cuh: SAT_PLAIN) is compiled for the default shape only
+template <int ROUNDS>
+KernelFn sat_plain_kernel(int block, int per_sm)
 {
+    if (block == TMC_DEFAULT_BLOCK_PLAIN && per_sm == 1) return tmc::photon_walk_kernel<ROUNDS, TMC_DEFAULT_BLOCK_PLAIN, 1, false, false, kPhotonsPerLane, true>;
+    return nullptr;
+}
+
+KernelFn pick_kernel(int rounds, int block, int per_sm, bool lane_private, bool radial, bool sat_plain = false)
+{
+    if (sat_plain && !lane_private && !radial) {
+        KernelFn fn = rounds == 10 ? sat_plain_kernel<10>(block, per_sm) : rounds == 7 ? sat_plain_kernel<7>(block, per_sm) : nullptr;
+        if (fn) return fn;      // else: the per-lane-slot variant of that shape (same tallies)
+    }
     if (radial) return rounds == 10 ? radial_kernel<10>(block, per_sm, lane_private) : rounds == 7 ? radial_kernel<7>(block, per_sm, lane_private) : nullptr;
     switch (rounds) {
     case 7: return lane_private ? kernel_for_block<7, true>(block, per_sm) : kernel_for_block<7, false>(block, per_sm);
@@ -422,10 +435,30 @@ double shells_per_mfp_of(const tmc_params* p)
 
 double g_launch_us = 0.0;   // host time inside cudaLaunchKernel since the last trace line (TMC_TRACE)
 
+// An upper bound on the share of scatter events beyond the grid radius R = SHELLS / shells_per_mfp mean free paths.
+// A photon's n-th position is a sum of n isotropic steps of Exp(1) length; one coordinate X of it has the moment
+// generating function (atanh(s) / s)^n, so P(|r| > R) <= 6 min_s exp(-s R / sqrt(3)) (atanh(s) / s)^n (Chernoff, three
+// coordinates, two signs), with n = the events of generations 0 .. 5 (deeper ones hold 1e-6 of the photons).
+double overflow_bound(const Plan& pl, uint32_t shells)
+{
+    const double radius = static_cast<double>(shells) / static_cast<double>(pl.shells_per_mfp);
+    double n = 0.0;
+    for (uint32_t i = 0; i < pl.n_gen && i < 6u; ++i) n += static_cast<double>(pl.gen[i].n_events);
+    double best = 1.0;
+    for (double s = 0.05; s < 0.96; s += 0.05) {
+        const double b = 6.0 * std::exp(-s * radius / std::sqrt(3.0) + n * std::log(std::atanh(s) / s));
+        if (b < best) best = b;
+    }
+    return best;
+}
+
 int configure_launch(const tmc_params* p, const Plan& pl, int device_sms, uint64_t count, uint32_t flush_override, LaunchCfg* cfg)
 {
     bool lane_private = p->shells <= tmc::kLanePrivateMaxShells;
-    if (g.opt.tally_layout == 1) lane_private = false;
+    if (g.opt.tally_layout == 1 || g.opt.tally_layout == 3) lane_private = false;
+    // one histogram per block: the integer clamp to per-lane overflow slots costs an instruction per event; where no
+    // photon leaves the grid in practice the saturating clamp (all of them into the ONE word of the last shell) is free
+    const bool sat_plain = !lane_private && (g.opt.tally_layout == 3 || (g.opt.tally_layout == 0 && overflow_bound(pl, p->shells) < 1e-6));
     if (g.opt.tally_layout == 2 && !lane_private)
         return fail(TMC_ERR_BAD_ARG, "SHELLS=%u is too large for lane-private tallies (max %u)", p->shells, tmc::kLanePrivateMaxShells);
     int block = g.opt.block_threads;
@@ -438,8 +471,8 @@ int configure_launch(const tmc_params* p, const Plan& pl, int device_sms, uint64
     const int smem_fit = static_cast<int>((227u * 1024u) / (smem + 1024u));
     if (want > smem_fit) want = smem_fit;
     KernelFn fn = nullptr;
-    for (int c = want; c >= 1 && !fn; --c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private, g.opt.walk_mode == 1);   // largest budget <= want
-    for (int c = want + 1; c <= 3 && !fn; ++c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private, g.opt.walk_mode == 1);   // else the next one
+    for (int c = want; c >= 1 && !fn; --c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private, g.opt.walk_mode == 1, sat_plain);   // largest budget <= want
+    for (int c = want + 1; c <= 3 && !fn; ++c) fn = pick_kernel(g.opt.philox_rounds, block, c, lane_private, g.opt.walk_mode == 1, sat_plain);   // else the next one
     if (!fn)
         return fail(TMC_ERR_BAD_ARG, "no kernel for philox_rounds=%d block_threads=%d blocks_per_sm=%d walk_mode=%d", g.opt.philox_rounds,
                     block, g.opt.blocks_per_sm, g.opt.walk_mode);
@@ -486,7 +519,7 @@ int configure_launch(const tmc_params* p, const Plan& pl, int device_sms, uint64
             // wrap; the 2^31 check catches the rest: tmc_photons* repeat the range with a shorter interval,
             // callers of tmc_photons_device must test the flag word, e.g. with tmc_device_tallies_check).
             double share = 2.0 / static_cast<double>(shells_per_mfp_of(p));
-            if (share > 1.0) share = 1.0;
+            if (share > 1.0 || g.opt.tally_layout == 3) share = 1.0;   // forced single overflow word: it may take every event
             const double blocks = 2147483648.0 / (32.0 * ppl * static_cast<double>(warps) * ev_per_flush * share * (d0 + 1.0));
             flush = blocks > 64.0 ? 64u : (blocks < 1.0 ? 1u : static_cast<uint32_t>(blocks));
         }
@@ -986,7 +1019,8 @@ int tmc_set_option(const char* name, long long value)
         if (value < 1 || value > 4096) return fail(TMC_ERR_BAD_ARG, "batch_capacity must be 1..4096");
         g.opt.batch_capacity = static_cast<int>(value);
     } else if (n == "tally_layout") {
-        if (value < 0 || value > 2) return fail(TMC_ERR_BAD_ARG, "tally_layout must be 0 (auto), 1 (plain) or 2 (lane-private)");
+        if (value < 0 || value > 3)
+            return fail(TMC_ERR_BAD_ARG, "tally_layout must be 0 (auto), 1 (plain, per-lane overflow slots), 2 (lane-private) or 3 (plain, saturating clamp)");
         g.opt.tally_layout = static_cast<int>(value);
     } else {
         return fail(TMC_ERR_BAD_ARG, "unknown option '%s'", name);

@@ -264,13 +264,17 @@ __device__ __noinline__ uint32_t drain_slice(uint32_t* bins, unsigned long long*
 //         NOT the path the north star names (it skips the position update and the direction
 //         resampling), never used for the headline or the roofline figure.
 // PPL:    photons per lane (independent dependency chains per thread); a cohort is 32 * PPL photons.
-template <int ROUNDS, int BLOCK, int MIN_BLOCKS, bool LANE_PRIVATE, bool RADIAL = false, int PPL = TMC_PPL>
+// SAT_PLAIN: the one-histogram layout with the saturating clamp of the lane-private layout instead of the integer clamp to
+//         per-lane overflow slots (one VIMNMX per event less).  Every |r| >= 1 then lands in the ONE word of shell SHELLS-1, which
+//         serialises the lanes that are out there: for grids no photon leaves in practice (the host decides, tmc_api.cu).
+template <int ROUNDS, int BLOCK, int MIN_BLOCKS, bool LANE_PRIVATE, bool RADIAL = false, int PPL = TMC_PPL, bool SAT_PLAIN = false>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __grid_constant__ WalkArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];     // [gap | direction table 64 KB | histograms]
     __shared__ uint32_t drain_ticket;
     constexpr uint32_t WARPS = BLOCK / 32;
     constexpr uint32_t COHORT = 32u * PPL;
+    constexpr bool SAT_CLAMP = LANE_PRIVATE || SAT_PLAIN;   // the clamp of photon.c:27-29 as the .sat of r^2's last FFMA
     static_assert(2u * COHORT <= kQueueCap, "a survivor queue must hold two cohorts");
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
@@ -346,10 +350,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     // drop (photon.c:26-29): shell = min(trunc(|r| * shells_per_mfp), SHELLS-1).  Positions are in units of the
     // grid radius, so |r|^2 saturated to 1 by the .sat of its last FFMA IS the clamp to the overflow bin (every
     // |r| >= 1 lands in shell SHELLS-1); trunc(|r| * shell_scale) without F2I: add 2^23 rounding toward zero, the
-    // mantissa is the integer.  The one-histogram layout clamps the raw bits instead, to per-lane overflow slots.
+    // mantissa is the integer.  The one-histogram layout clamps the raw bits instead, to per-lane overflow slots
+    // (unless SAT_PLAIN).
     auto radius_sq = [&](float x, float y, float z) {
         const float r2 = fmaf(z, z, fmaf(y, y, x * x));
-        return LANE_PRIVATE ? __saturatef(r2) : r2;
+        return SAT_CLAMP ? __saturatef(r2) : r2;
     };
     // spin + hop (photon.c:35-43 sampled directly, photon.c:22-24): L = log2(xi) <= 0, pol = kappa * (-ln2 cos, -ln2 sin)(theta),
     // azi = (cos, sin)(phi); the step t = -ln2 * L is folded into the polar entry
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
     };
     auto shell_bits = [&](float rad) {
         const uint32_t sb = __float_as_uint(__fmaf_rz(rad, a.shell_scale, 8388608.0f));
-        return LANE_PRIVATE ? sb : min(sb, clamp_bits);
+        return SAT_CLAMP ? sb : min(sb, clamp_bits);
     };
 
     // The lane's PPL photons share packed instructions in pairs (2p, 2p+1); an odd last photon goes scalar.
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) photon_walk_kernel(const __
             uint32_t sb0, sb1 = 0u;
             if ((kPacked & 4) && j + 1 < PPL) {                                         // both shell numbers by one FFMA2.RZ
                 fma2_rz_bits(rad[j], rad[j + 1], a.shell_scale, 8388608.0f, sb0, sb1);
-                if constexpr (!LANE_PRIVATE) {
+                if constexpr (!SAT_CLAMP) {
                     sb0 = min(sb0, clamp_bits);
                     sb1 = min(sb1, clamp_bits);
                 }
